@@ -1,0 +1,119 @@
+/*
+ * pynqs_b200.h -- C ABI of the B200-native VMC local-energy library (libpynqs_b200.so).
+ *
+ * Drop-in boundary for the operator API of the reference's `libs/C_extension`
+ * (stubs: libs/C_extension.pyi; pybind11 bindings: cpp_src/tensor/bind.cpp:317-391).
+ * Every entry point takes plain pointers and sizes -- no torch / pybind types -- so the
+ * reference-side binding is a ctypes stub (see INTEGRATION.md and pynqs_b200/C_extension.py).
+ *
+ * Conventions
+ *  - All data pointers are DEVICE pointers on the current CUDA device unless stated otherwise;
+ *    the caller sets the device (one process per GPU) and passes the stream to launch on.
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *  - ONVs are `uint8[rows, 8*L]` contiguous, L = ceil(sorb/64), reinterpreted as little-endian
+ *    `uint64[rows, L]`; spin orbital s = bit (s % 64) of word (s / 64); even = alpha, odd = beta
+ *    (cpp_src/tensor/cpu_tensor.cpp:8-44, cpp_src/cpu/excitation.cpp:47-48).
+ *  - `dtype`: PYNQS_F32 / PYNQS_F64 = element type of h1e, h2e and of the H output
+ *    (the reference dispatches on h1e's dtype, cpp_src/tensor/cuda_tensor.cpp:186-199).
+ *  - Every function returns 0 on success, a PYNQS_E* code otherwise; pynqs_last_error() gives
+ *    the message of the calling thread's last failure.  Nothing is allocated for the caller;
+ *    scratch comes from caller-provided workspaces whose sizes the *_bytes functions report.
+ *  - Kernels are asynchronous w.r.t. the host; no call synchronises the device.
+ */
+#ifndef PYNQS_B200_H
+#define PYNQS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PYNQS_ABI_VERSION 1
+
+enum { PYNQS_F32 = 0, PYNQS_F64 = 1 };
+
+enum {
+  PYNQS_OK = 0,
+  PYNQS_EVALUE = 1,    /* bad argument  -> Python ValueError  (std::length_error in bind.cpp:282-291) */
+  PYNQS_EOVERFLOW = 2, /* too many electrons/virtuals -> OverflowError (bind.cpp:292-301) */
+  PYNQS_ECUDA = 3,     /* CUDA runtime / launch failure -> RuntimeError (cuda_handle_error.h:8-39) */
+  PYNQS_EWORKSPACE = 4 /* workspace too small -> RuntimeError */
+};
+
+/* compile-time limits of this build; the reference exports the same three module attributes
+ * (bind.cpp:382-384) but fixes L at compile time -- here L in {1,2,3} is dispatched at run time. */
+#define PYNQS_MAX_SORB_LEN 3
+#define PYNQS_MAX_SORB 192
+#define PYNQS_MAX_NELE 120
+
+int pynqs_abi_version(void);
+const char *pynqs_last_error(void);
+
+/* replaces check_sorb (bind.cpp:282-301): PYNQS_EVALUE if sorb not in (0, 192],
+ * PYNQS_EOVERFLOW if nele > PYNQS_MAX_NELE.  The reference's per-L virtual-orbital cap
+ * (MAX_NV = 40 L) is not needed by these kernels and is not enforced. */
+int pynqs_check_sorb(int sorb, int nele);
+
+/* replaces get_Num_SinglesDoubles (cpp_src/cpu/excitation.cpp:8-16); *nsd excludes the bra row. */
+int pynqs_num_sd(int sorb, int noA, int noB, int64_t *nsd);
+
+/* replaces tensor_to_onv (bind.cpp:9-22, cpu_tensor.cpp:8-44; kernel.cu:14-37):
+ * states uint8[n, sorb] (value 1 = occupied) -> onv uint8[n, 8L]. */
+int pynqs_tensor_to_onv(const uint8_t *states, int64_t n, int sorb, uint8_t *onv, void *stream);
+
+/* replaces onv_to_tensor (bind.cpp:24-37, cpu_tensor.cpp:46-88; kernel.cu:39-64):
+ * onv uint8[n, 8L] -> out dtype[n, sorb], +1 occupied / -1 empty. */
+int pynqs_onv_to_tensor(const uint8_t *onv, int64_t n, int sorb, void *out, int dtype, void *stream);
+
+/* replaces get_comb_tensor (bind.cpp:66-83, cuda_tensor.cpp:217-266; kernels K1+K2):
+ * comb uint8[n, M, 8L], M = nsd + 1, row 0 = bra.  If states != NULL it receives the
+ * flag_bit=True output double[n, M, sorb] of +-1 (cpu_tensor.cpp:186-190). */
+int pynqs_comb(const uint8_t *bra, int64_t n, int sorb, int noA, int noB, uint8_t *comb, double *states,
+               void *stream);
+
+/* replaces get_comb_hij_fused (bind.cpp:239-250, cuda_tensor.cpp:162-215; kernels K1+K5):
+ * comb uint8[n, M, 8L] and hmat dtype[n, M]; hmat[:,0] = <x|H|x> over the first `nele`
+ * occupied orbitals (cpu_tensor.cpp:260-261). */
+int pynqs_comb_hij_fused(const uint8_t *bra, const void *h1e, const void *h2e, int64_t n, int sorb, int nele,
+                         int noA, int noB, uint8_t *comb, void *hmat, int dtype, void *stream);
+
+/* replaces get_hij_torch (bind.cpp:39-64, cuda_tensor.cpp:97-141; kernels K3/K4):
+ * ket3d != 0: ket uint8[n, m, 8L], out[i,j] = <bra_i|H|ket_ij>;
+ * ket3d == 0: ket uint8[m, 8L],    out[i,j] = <bra_i|H|ket_j>.  More than a double excitation -> 0. */
+int pynqs_hij(const uint8_t *bra, const uint8_t *ket, const void *h1e, const void *h2e, int64_t n, int64_t m,
+              int ket3d, int sorb, int nele, void *out, int dtype, void *stream);
+
+/* replaces wavefunction_lut (bind.cpp:220-237, cuda_tensor.cpp:436-487; kernel K6): classic
+ * binary search (same probe sequence as cpu_tensor.cpp:589-640, so identical results even for
+ * duplicate keys) of n queries in key uint8[N, 8L] sorted ascending as little-endian
+ * multi-word integers.  idx int64[n] (-1 if absent), mask uint8/bool[n]. */
+int pynqs_lut(const uint8_t *key, int64_t N, const uint8_t *onv, int64_t n, int L, int64_t *idx, uint8_t *mask,
+              void *stream);
+
+/* Hash index over a sorted UNIQUE key table -- an internal accelerator for the two functions
+ * below; results are identical to pynqs_lut.  If the table holds duplicates the build records
+ * it and the lookups fall back to the classic search on the device (no host round trip). */
+int pynqs_hash_bytes(int64_t N, int L, int64_t *bytes);
+int pynqs_hash_build(const uint8_t *key, int64_t N, int L, void *hash_ws, int64_t hash_bytes, void *stream);
+int pynqs_lut_hashed(const uint8_t *key, int64_t N, const uint8_t *onv, int64_t n, int L, const void *hash_ws,
+                     int64_t *idx, uint8_t *mask, void *stream);
+
+/* Additive op: the whole sample-space local energy of vmc/energy/eloc.py:326-397 in one pass,
+ * never materialising comb / Hmat:  for each sample x, psi0 = table value of x (0 if absent),
+ *   eloc = sum over x' in {x} U SD(x) found in the table of (psi(x') / psi0) * <x|H|x'>.
+ * psi: double[N] (psi_complex == 0) or interleaved complex128[N]; eloc / psi0 likewise [n].
+ * scratch: pynqs_eloc_scratch_bytes(n, ...) bytes.  h1e/h2e are float64. */
+int pynqs_eloc_scratch_bytes(int64_t n, int sorb, int noA, int noB, int psi_complex, int64_t *bytes);
+int pynqs_eloc_sample_space(const uint8_t *bra, int64_t n, const double *h1e, const double *h2e, int sorb,
+                            int nele, int noA, int noB, const uint8_t *key, const void *psi, int psi_complex,
+                            int64_t N, const void *hash_ws, void *scratch, int64_t scratch_bytes, void *eloc,
+                            void *psi0, void *stream);
+
+/* number of kernel launches issued by this library in this process (bench.py's gpu_launches). */
+int64_t pynqs_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PYNQS_B200_H */

@@ -1,0 +1,398 @@
+"""Host mirror of the reference operator API `libs.C_extension` (stubs: libs/C_extension.pyi;
+bindings: cpp_src/tensor/bind.cpp:317-391) on top of libpynqs_b200.so.
+
+Same function names, keyword names, tensor layouts, dtypes and exception types.  Differences,
+all deliberate:
+  * CUDA only -- CPU tensors raise RuntimeError (the product has no CPU fallback);
+  * MAX_SORB_LEN is dispatched at run time from the tensor width (1, 2 or 3 words);
+  * shape problems raise ValueError instead of tripping an assert / exit(1);
+  * kernels run on torch's current stream of the tensor's device.
+Outputs are allocated with torch (caching allocator); the C side never allocates.
+"""
+from __future__ import annotations
+
+import weakref
+from typing import Tuple
+
+import numpy as np
+import torch
+from torch import Tensor
+
+from . import _lib
+from ._lib import i64, vp
+
+MAX_SORB_LEN: int = 3
+MAX_SORB: int = 192
+MAX_NELE: int = 120
+
+# queries >= this (and >= N / 8) switch wavefunction_lut from the classic search to the hash index
+_HASH_MIN_QUERIES = 1 << 15
+
+
+# ------------------------------------------------------------------------------------------------
+def _need_cuda(*tensors: Tensor) -> torch.device:
+    dev = None
+    for t in tensors:
+        if not isinstance(t, Tensor):
+            raise TypeError(f"expected torch.Tensor, got {type(t)}")
+        if not t.is_cuda:
+            raise RuntimeError(
+                "pynqs_b200 ops are CUDA-only (no CPU fallback): move the tensors to a B200 device"
+            )
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise RuntimeError(f"tensors on different devices: {dev} vs {t.device}")
+    return dev
+
+
+def _contig(t: Tensor, name: str) -> None:
+    if not t.is_contiguous():
+        raise RuntimeError(f"{name} must be contiguous")  # CHECK_CONTIGUOUS, bind.cpp:45-48,72
+
+
+def _onv_words(t: Tensor, name: str) -> int:
+    if t.dtype != torch.uint8:
+        raise ValueError(f"{name} must be torch.uint8, got {t.dtype}")
+    w = t.size(-1)
+    if w % 8 or not 1 <= w // 8 <= MAX_SORB_LEN:
+        raise ValueError(f"{name}: last dim {w} must be 8, 16 or 24 bytes")
+    return w // 8
+
+
+def _check_width(t: Tensor, sorb: int, name: str) -> int:
+    L = _onv_words(t, name)
+    if L != (sorb - 1) // 64 + 1:
+        raise ValueError(f"{name}: width {8 * L} bytes does not match sorb = {sorb}")  # bind.cpp:73-75
+    return L
+
+
+def _stream(dev: torch.device):
+    return vp(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def _fdtype(h1e: Tensor, h2e: Tensor) -> int:
+    if h1e.dtype != h2e.dtype:
+        raise ValueError(f"h1e ({h1e.dtype}) and h2e ({h2e.dtype}) must have the same dtype")
+    if h1e.dtype == torch.float64:
+        return _lib.F64
+    if h1e.dtype == torch.float32:
+        return _lib.F32
+    raise ValueError(f"h1e/h2e must be float32 or float64, got {h1e.dtype}")  # AT_DISPATCH_FLOATING_TYPES
+
+
+def _check_integrals(h1e: Tensor, h2e: Tensor, sorb: int) -> None:
+    pair = sorb * (sorb - 1) // 2
+    if h1e.numel() != sorb * sorb or h2e.numel() != pair * (pair + 1) // 2:
+        raise ValueError(
+            f"packed integrals have {h1e.numel()} / {h2e.numel()} elements, expected "
+            f"{sorb * sorb} / {pair * (pair + 1) // 2} for sorb = {sorb}"
+        )
+
+
+# ------------------------------------------------------------------------------------------------
+def check_sorb(sorb: int, nele: int) -> None:
+    """check_sorb (bind.cpp:282-301): ValueError for an unsupported sorb, OverflowError for too many electrons."""
+    _lib.check(_lib.load().pynqs_check_sorb(int(sorb), int(nele)))
+
+
+def get_Num_SinglesDoubles(sorb: int, noA: int, noB: int) -> int:
+    """number of singles + doubles (cpp_src/cpu/excitation.cpp:8-16; utils/public_function.py:132-144)."""
+    out = _lib.ctypes.c_int64()
+    _lib.check(_lib.load().pynqs_num_sd(int(sorb), int(noA), int(noB), _lib.ctypes.byref(out)))
+    return int(out.value)
+
+
+def tensor_to_onv(bra: Tensor, sorb: int) -> Tensor:
+    """0/1 uint8 states [n, sorb] (or [sorb]) -> packed ONV uint8 [n, 8L]   (C_extension.pyi:5-24)."""
+    dev = _need_cuda(bra)
+    _contig(bra, "bra")
+    if bra.dtype != torch.uint8 or bra.dim() not in (1, 2):
+        raise ValueError("bra must be a 1-D or 2-D torch.uint8 tensor")
+    L = (sorb - 1) // 64 + 1
+    if bra.numel() == 0:
+        return torch.empty((0, 8 * L), dtype=torch.uint8, device=dev)
+    if bra.numel() % sorb:
+        raise ValueError(f"bra has {bra.numel()} elements, not a multiple of sorb = {sorb}")
+    n = bra.numel() // sorb
+    out = torch.empty((n, 8 * L), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().pynqs_tensor_to_onv(vp(bra.data_ptr()), i64(n), int(sorb), vp(out.data_ptr()), _stream(dev)))
+    return out
+
+
+def onv_to_tensor(bra: Tensor, sorb: int) -> Tensor:
+    """packed ONV uint8 [n, 8L] (or [8L]) -> +-1 tensor [n, sorb] in torch.get_default_dtype()
+    (C_extension.pyi:26-45, cpu_tensor.cpp:55)."""
+    dev = _need_cuda(bra)
+    _contig(bra, "bra")
+    if bra.dim() not in (1, 2):
+        raise ValueError("bra must be 1-D or 2-D")
+    L = _onv_words(bra, "bra")
+    bra2 = bra.view(-1, 8 * L)
+    dtype = torch.get_default_dtype()
+    if dtype not in (torch.float32, torch.float64):
+        raise ValueError(f"default dtype {dtype} unsupported")
+    n = bra2.size(0)
+    out = torch.empty((n, sorb), dtype=dtype, device=dev)
+    if n == 0:
+        return out
+    code = _lib.F64 if dtype == torch.float64 else _lib.F32
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().pynqs_onv_to_tensor(vp(bra2.data_ptr()), i64(n), int(sorb), vp(out.data_ptr()), code, _stream(dev)))
+    return out
+
+
+def get_comb_tensor(bra: Tensor, sorb: int, nele: int, noA: int, noB: int, flag_bit: bool = False) -> Tuple[Tensor, Tensor]:
+    """All singles and doubles of every bra (C_extension.pyi:47-90): comb uint8 [n, M, 8L], row 0 = bra.
+    Second value: +-1 states double [n, M, sorb] if flag_bit else ones(1) on the CPU, exactly as the
+    reference returns it (cpu_tensor.cpp:191, cuda_tensor.cpp:247)."""
+    dev = _need_cuda(bra)
+    _contig(bra, "bra")
+    if bra.dim() == 1:
+        bra = bra.view(1, -1)
+    L = _check_width(bra, sorb, "bra")
+    M = get_Num_SinglesDoubles(sorb, noA, noB) + 1
+    n = bra.size(0)
+    comb = torch.empty((n, M, 8 * L), dtype=torch.uint8, device=dev)
+    states = torch.empty((n, M, sorb), dtype=torch.float64, device=dev) if flag_bit else None
+    if n:
+        with torch.cuda.device(dev):
+            _lib.check(
+                _lib.load().pynqs_comb(
+                    vp(bra.data_ptr()), i64(n), int(sorb), int(noA), int(noB), vp(comb.data_ptr()),
+                    vp(states.data_ptr() if flag_bit else None), _stream(dev),
+                )
+            )
+    if not flag_bit:
+        states = torch.ones(1, dtype=torch.float64)
+    return comb, states
+
+
+def get_comb_hij_fused(bra: Tensor, h1e: Tensor, h2e: Tensor, sorb: int, nele: int, noA: int, noB: int) -> Tuple[Tensor, Tensor]:
+    """Fused enumeration + <x|H|x'> (C_extension.pyi:125-137): (comb uint8 [n, M, 8L], Hmat [n, M])."""
+    dev = _need_cuda(bra, h1e, h2e)
+    for t, nm in ((bra, "bra"), (h1e, "h1e"), (h2e, "h2e")):
+        _contig(t, nm)
+    if bra.dim() == 1:
+        bra = bra.view(1, -1)
+    L = _check_width(bra, sorb, "bra")
+    code = _fdtype(h1e, h2e)
+    _check_integrals(h1e, h2e, sorb)
+    M = get_Num_SinglesDoubles(sorb, noA, noB) + 1
+    n = bra.size(0)
+    comb = torch.empty((n, M, 8 * L), dtype=torch.uint8, device=dev)
+    hmat = torch.empty((n, M), dtype=h1e.dtype, device=dev)
+    if n:
+        with torch.cuda.device(dev):
+            _lib.check(
+                _lib.load().pynqs_comb_hij_fused(
+                    vp(bra.data_ptr()), vp(h1e.data_ptr()), vp(h2e.data_ptr()), i64(n), int(sorb), int(nele),
+                    int(noA), int(noB), vp(comb.data_ptr()), vp(hmat.data_ptr()), code, _stream(dev),
+                )
+            )
+    return comb, hmat
+
+
+def get_hij_torch(bra: Tensor, ket: Tensor, h1e: Tensor, h2e: Tensor, sorb: int, nele: int) -> Tensor:
+    """<bra|H|ket> (C_extension.pyi:92-123): ket 3-D [n, m, 8L] -> local-energy layout [n, m];
+    ket 2-D [m, 8L] -> matrix [n, m].  dtype/device of h1e."""
+    dev = _need_cuda(bra, ket, h1e, h2e)
+    for t, nm in ((bra, "bra"), (ket, "ket"), (h1e, "h1e"), (h2e, "h2e")):
+        _contig(t, nm)
+    if bra.dim() != 2 or ket.dim() not in (2, 3):
+        raise ValueError("bra must be 2-D and ket 2-D or 3-D")
+    L = _check_width(bra, sorb, "bra")
+    if _onv_words(ket, "ket") != L:
+        raise ValueError("bra and ket widths differ")
+    code = _fdtype(h1e, h2e)
+    _check_integrals(h1e, h2e, sorb)
+    n = bra.size(0)
+    ket3d = ket.dim() == 3
+    if ket3d and ket.size(0) != n:
+        raise ValueError(f"ket batch {ket.size(0)} != bra batch {n}")
+    m = ket.size(1) if ket3d else ket.size(0)
+    out = torch.empty((n, m), dtype=h1e.dtype, device=dev)
+    if n and m:
+        with torch.cuda.device(dev):
+            _lib.check(
+                _lib.load().pynqs_hij(
+                    vp(bra.data_ptr()), vp(ket.data_ptr()), vp(h1e.data_ptr()), vp(h2e.data_ptr()), i64(n), i64(m),
+                    int(ket3d), int(sorb), int(nele), vp(out.data_ptr()), code, _stream(dev),
+                )
+            )
+    return out
+
+
+# ---- hash index over a sorted key table ---------------------------------------------------------
+class HashIndex:
+    """Device hash index of a sorted unique key table (internal accelerator of the lookups)."""
+
+    def __init__(self, bra_key: Tensor):
+        dev = _need_cuda(bra_key)
+        _contig(bra_key, "bra_key")
+        self.L = _onv_words(bra_key, "bra_key")
+        self.N = bra_key.size(0)
+        nbytes = _lib.ctypes.c_int64()
+        _lib.check(_lib.load().pynqs_hash_bytes(i64(self.N), self.L, _lib.ctypes.byref(nbytes)))
+        self.workspace = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(
+                _lib.load().pynqs_hash_build(
+                    vp(bra_key.data_ptr()), i64(self.N), self.L, vp(self.workspace.data_ptr()), i64(nbytes.value), _stream(dev)
+                )
+            )
+
+    @property
+    def nbytes(self) -> int:
+        return self.workspace.numel()
+
+
+_hash_cache: dict = {}
+
+
+def _cached_hash(bra_key: Tensor) -> HashIndex:
+    """Per-tensor-object cache: valid while the same tensor object is alive and unmodified."""
+    k = id(bra_key)
+    ent = _hash_cache.get(k)
+    if ent is not None:
+        ref, version, ptr, hidx = ent
+        if ref() is bra_key and version == bra_key._version and ptr == bra_key.data_ptr():
+            return hidx
+    hidx = HashIndex(bra_key)
+    _hash_cache[k] = (weakref.ref(bra_key, lambda _r, k=k: _hash_cache.pop(k, None)), bra_key._version, bra_key.data_ptr(), hidx)
+    return hidx
+
+
+def wavefunction_lut(bra_key: Tensor, onv: Tensor, sorb: int, little_endian: bool = True, *, hash_index: HashIndex | None = None) -> Tuple[Tensor, Tensor]:
+    """Index of every onv row in the sorted key table (C_extension.pyi:305-357): (idx int64 [n]
+    with -1 for absent rows, mask bool [n]).  The ONV width comes from the tensors, not from
+    `sorb` (DetLUT passes a prefix length, utils/det_helper/determinant_lut.py:285-291)."""
+    if not little_endian:
+        raise NotImplementedError("little_endian=False is broken in the reference (cpu_tensor.cpp:613) and never used")
+    dev = _need_cuda(bra_key, onv)
+    _contig(bra_key, "bra_key")
+    _contig(onv, "onv")
+    L = _onv_words(bra_key, "bra_key")
+    if onv.dim() != 2 or _onv_words(onv, "onv") != L:
+        raise ValueError("onv must be 2-D with the same width as bra_key")  # exit(1) in cuda_tensor.cpp:445-449
+    n, N = onv.size(0), bra_key.size(0)
+    idx = torch.empty(n, dtype=torch.int64, device=dev)
+    mask = torch.empty(n, dtype=torch.bool, device=dev)
+    if n == 0:
+        return idx, mask
+    lib = _lib.load()
+    if hash_index is None and n >= _HASH_MIN_QUERIES and 8 * n >= N and N < (1 << 32):
+        hash_index = _cached_hash(bra_key)
+    with torch.cuda.device(dev):
+        if hash_index is not None:
+            _lib.check(
+                lib.pynqs_lut_hashed(
+                    vp(bra_key.data_ptr()), i64(N), vp(onv.data_ptr()), i64(n), L, vp(hash_index.workspace.data_ptr()),
+                    vp(idx.data_ptr()), vp(mask.data_ptr()), _stream(dev),
+                )
+            )
+        else:
+            _lib.check(
+                lib.pynqs_lut(vp(bra_key.data_ptr()), i64(N), vp(onv.data_ptr()), i64(n), L, vp(idx.data_ptr()), vp(mask.data_ptr()), _stream(dev))
+            )
+    return idx, mask
+
+
+def eloc_sample_space(
+    bra: Tensor, h1e: Tensor, h2e: Tensor, sorb: int, nele: int, noA: int, noB: int,
+    bra_key: Tensor, wf_value: Tensor, hash_index: HashIndex | None = None,
+) -> Tuple[Tensor, Tensor]:
+    """Additive op: the whole sample-space local energy of vmc/energy/eloc.py:326-397 in one pass.
+    Returns (eloc [n], psi0 [n]) in wf_value's dtype (float64 or complex128).  bra_key must be the
+    sorted unique table and wf_value its values in the same order."""
+    dev = _need_cuda(bra, h1e, h2e, bra_key, wf_value)
+    for t, nm in ((bra, "bra"), (h1e, "h1e"), (h2e, "h2e"), (bra_key, "bra_key"), (wf_value, "wf_value")):
+        _contig(t, nm)
+    L = _check_width(bra, sorb, "bra")
+    if _onv_words(bra_key, "bra_key") != L:
+        raise ValueError("bra and bra_key widths differ")
+    if h1e.dtype != torch.float64 or h2e.dtype != torch.float64:
+        raise ValueError("eloc_sample_space needs float64 integrals")
+    _check_integrals(h1e, h2e, sorb)
+    if wf_value.dtype not in (torch.float64, torch.complex128) or wf_value.numel() != bra_key.size(0):
+        raise ValueError("wf_value must be float64/complex128 with one value per key")
+    cplx = int(wf_value.dtype == torch.complex128)
+    n, N = bra.size(0), bra_key.size(0)
+    eloc = torch.empty(n, dtype=wf_value.dtype, device=dev)
+    psi0 = torch.empty(n, dtype=wf_value.dtype, device=dev)
+    if n == 0:
+        return eloc, psi0
+    if hash_index is None:
+        hash_index = _cached_hash(bra_key)
+    lib = _lib.load()
+    nbytes = _lib.ctypes.c_int64()
+    _lib.check(lib.pynqs_eloc_scratch_bytes(i64(n), int(sorb), int(noA), int(noB), cplx, _lib.ctypes.byref(nbytes)))
+    scratch = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(
+            lib.pynqs_eloc_sample_space(
+                vp(bra.data_ptr()), i64(n), vp(h1e.data_ptr()), vp(h2e.data_ptr()), int(sorb), int(nele), int(noA), int(noB),
+                vp(bra_key.data_ptr()), vp(wf_value.data_ptr()), cplx, i64(N), vp(hash_index.workspace.data_ptr()),
+                vp(scratch.data_ptr()), i64(nbytes.value), vp(eloc.data_ptr()), vp(psi0.data_ptr()), _stream(dev),
+            )
+        )
+    return eloc, psi0
+
+
+# ---- names outside the hot path that callers import -----------------------
+def merge_rank_sample(idx: Tensor, counts: Tensor, split_idx: Tensor, length: int) -> Tensor:
+    """merge_counts[idx[i]] += counts[i] (C_extension.pyi:256-279); torch index_add_ (atomic, unlike
+    the reference's non-atomic kernel, cuda/kernel.cu:520-536)."""
+    out = torch.zeros(length, dtype=counts.dtype, device=counts.device)
+    return out.index_add_(0, idx, counts)
+
+
+def compress_h1e_h2e(h1e: np.ndarray, h2e: np.ndarray, sorb: int):
+    """dense spin-orbital <pq||rs> -> packed 1-D arrays (cpp_src/tensor/integral.cpp:6-60)."""
+    h1e = np.asarray(h1e, dtype=np.float64)
+    h2e = np.asarray(h2e, dtype=np.float64)
+    pair = sorb * (sorb - 1) // 2
+    ii, jj = np.tril_indices(sorb, -1)  # i > j, ordered by pair index i(i-1)/2 + j
+    block = h2e[ii[:, None], jj[:, None], ii[None, :], jj[None, :]]  # [pair, pair] = <ij||kl>
+    r, c = np.tril_indices(pair)
+    return h1e.reshape(-1).copy(), block[r, c].copy()
+
+
+def decompress_h1e_h2e(h1e: np.ndarray, h2e: np.ndarray, sorb: int):
+    """packed -> dense with the antisymmetry signs; entries with i == j or k == l are 0
+    (the reference leaves them uninitialised)."""
+    pair = sorb * (sorb - 1) // 2
+    sq = np.zeros((pair, pair))
+    r, c = np.tril_indices(pair)
+    sq[r, c] = h2e
+    sq[c, r] = h2e
+    ii, jj = np.tril_indices(sorb, -1)
+    dense = np.zeros((sorb,) * 4)
+    I, J = ii[:, None], jj[:, None]
+    K, Lx = ii[None, :], jj[None, :]
+    dense[I, J, K, Lx] = sq
+    dense[J, I, K, Lx] = -sq
+    dense[I, J, Lx, K] = -sq
+    dense[J, I, Lx, K] = sq
+    return np.asarray(h1e, dtype=np.float64).reshape(sorb, sorb).copy(), dense
+
+
+def _not_on_path(name: str):
+    def f(*_a, **_k):
+        raise NotImplementedError(
+            f"{name} is outside the local-energy hot path (SURVEY.md section 8) and is not provided by pynqs_b200"
+        )
+
+    f.__name__ = name
+    return f
+
+
+spin_flip_rand = _not_on_path("spin_flip_rand")
+MCMC_sample = _not_on_path("MCMC_sample")
+permute_sgn = _not_on_path("permute_sgn")
+constrain_make_charts = _not_on_path("constrain_make_charts")
+convert_sites = _not_on_path("convert_sites")
+mps_vbatch = _not_on_path("mps_vbatch")
+wavefunction_lut_map = _not_on_path("wavefunction_lut_map")
+BKDR = _not_on_path("BKDR")

@@ -1,0 +1,74 @@
+"""ctypes binding of libpynqs_b200.so (C ABI: include/pynqs_b200.h).  No fallback: if the CUDA
+library is missing or cannot be loaded, importing an op raises."""
+from __future__ import annotations
+
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "csrc", "libpynqs_b200.so")
+
+# every symbol include/pynqs_b200.h declares (tests check the header against this list)
+SYMBOLS = [
+    "pynqs_abi_version", "pynqs_last_error", "pynqs_check_sorb", "pynqs_num_sd",
+    "pynqs_tensor_to_onv", "pynqs_onv_to_tensor", "pynqs_comb", "pynqs_comb_hij_fused", "pynqs_hij",
+    "pynqs_lut", "pynqs_hash_bytes", "pynqs_hash_build", "pynqs_lut_hashed",
+    "pynqs_eloc_scratch_bytes", "pynqs_eloc_sample_space", "pynqs_launch_count",
+]
+
+OK, EVALUE, EOVERFLOW, ECUDA, EWORKSPACE = 0, 1, 2, 3, 4
+F32, F64 = 0, 1
+
+_lib = None
+
+
+class PynqsLibraryMissing(RuntimeError):
+    pass
+
+
+def load() -> ctypes.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise PynqsLibraryMissing(
+            f"{LIB_PATH} not found: build it with `python -m pynqs_b200.build` (nvcc, sm_100a). "
+            "pynqs_b200 has no CPU or PyTorch fallback."
+        )
+    lib = ctypes.CDLL(LIB_PATH)
+    for s in SYMBOLS:
+        getattr(lib, s)  # raises AttributeError if the build is stale
+    lib.pynqs_last_error.restype = ctypes.c_char_p
+    lib.pynqs_launch_count.restype = ctypes.c_int64
+    if lib.pynqs_abi_version() != 1:
+        raise RuntimeError("libpynqs_b200.so ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def last_error() -> str:
+    return load().pynqs_last_error().decode()
+
+
+def check(rc: int) -> None:
+    """Map status codes to the exception types of the reference binding (bind.cpp:282-301)."""
+    if rc == OK:
+        return
+    msg = last_error()
+    if rc == EVALUE:
+        raise ValueError(msg)
+    if rc == EOVERFLOW:
+        raise OverflowError(msg)
+    raise RuntimeError(msg)
+
+
+def launch_count() -> int:
+    return int(load().pynqs_launch_count())
+
+
+def vp(x) -> ctypes.c_void_p:
+    return ctypes.c_void_p(x)
+
+
+def i64(x) -> ctypes.c_int64:
+    return ctypes.c_int64(int(x))

@@ -1,0 +1,236 @@
+// abi.cu -- extern "C" entry points of libpynqs_b200.so (declared in include/pynqs_b200.h).
+// Argument validation mirrors the reference binding layer (cpp_src/tensor/bind.cpp) with its
+// asserts / exit(1) turned into status codes.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+
+#include "../../include/pynqs_b200.h"
+#include "common.cuh"
+
+namespace pynqs {
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int check_launch(const char *what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: CUDA error %d (%s)", what, (int)e, cudaGetErrorString(e));
+    return PYNQS_ECUDA;
+  }
+  return 0;
+}
+
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// launchers implemented in the other translation units
+int launch_comb(const u64 *, u64 *, long long, const ExcGeom &, cudaStream_t);
+int launch_comb_hij_f64(const u64 *, const double *, const double *, u64 *, double *, long long, const ExcGeom &, cudaStream_t);
+int launch_comb_hij_f32(const u64 *, const float *, const float *, u64 *, float *, long long, const ExcGeom &, cudaStream_t);
+int launch_states(const u64 *, double *, long long, int, cudaStream_t);
+template <typename T>
+int launch_hij(const u64 *, const u64 *, const T *, const T *, T *, long long, long long, int, int, int, cudaStream_t);
+int launch_lut_classic(const u64 *, long long, const u64 *, long long, int, long long *, unsigned char *, cudaStream_t);
+long long hash_workspace_bytes(long long);
+int launch_hash_build(const u64 *, long long, int, void *, long long, cudaStream_t);
+int launch_lut_hashed(const u64 *, long long, const u64 *, long long, int, const void *, long long *, unsigned char *, cudaStream_t);
+long long eloc_scratch_bytes(long long, int, int);
+int launch_eloc(const u64 *, long long, const double *, const double *, const u64 *, const double *, int, long long,
+                const void *, void *, long long, double *, double *, const ExcGeom &, cudaStream_t);
+int launch_onv_to_tensor(const u64 *, void *, int, long long, int, cudaStream_t);
+int launch_tensor_to_onv(const unsigned char *, unsigned char *, long long, int, cudaStream_t);
+
+static int check_geometry(int sorb, int nele, int noA, int noB) {
+  if (sorb <= 0 || sorb > PYNQS_MAX_SORB) {
+    set_error("sorb = %d not in (0, %d]", sorb, PYNQS_MAX_SORB);
+    return PYNQS_EVALUE;
+  }
+  if (sorb & 1) {
+    set_error("sorb = %d must be even (alpha/beta interleaved spin orbitals)", sorb);
+    return PYNQS_EVALUE;
+  }
+  if (noA < 0 || noB < 0 || noA > sorb / 2 || noB > sorb / 2) {
+    set_error("noA = %d, noB = %d outside [0, sorb/2 = %d]", noA, noB, sorb / 2);
+    return PYNQS_EVALUE;
+  }
+  if (nele < 0 || nele > PYNQS_MAX_NELE) {
+    set_error("nele = %d outside [0, %d]", nele, PYNQS_MAX_NELE);
+    return PYNQS_EOVERFLOW;
+  }
+  return 0;
+}
+
+static int num_sd_checked(int sorb, int noA, int noB, long long *out) {
+  const long long k = sorb / 2, nvA = k - noA, nvB = k - noB;
+  const long long v = noA * nvA + noB * nvB + (long long)noA * (noA - 1) * nvA * (nvA - 1) / 4 +
+                      (long long)noB * (noB - 1) * nvB * (nvB - 1) / 4 + (long long)noA * noB * nvA * nvB;
+  *out = v;
+  if (v >= (1LL << 31) - 2) {
+    set_error("number of singles+doubles %lld does not fit the 31-bit row index", v);
+    return PYNQS_EOVERFLOW;
+  }
+  return 0;
+}
+
+}  // namespace pynqs
+
+using namespace pynqs;
+
+extern "C" {
+
+int pynqs_abi_version(void) { return PYNQS_ABI_VERSION; }
+
+const char *pynqs_last_error(void) { return g_err; }
+
+int64_t pynqs_launch_count(void) { return (int64_t)g_launches.load(); }
+
+int pynqs_check_sorb(int sorb, int nele) {
+  if (sorb <= 0 || sorb > PYNQS_MAX_SORB) {
+    set_error("Sorb error: sorb = %d not in (0, %d]", sorb, PYNQS_MAX_SORB);
+    return PYNQS_EVALUE;
+  }
+  if (nele > PYNQS_MAX_NELE) {
+    set_error("electron overflow: nele = %d > %d", nele, PYNQS_MAX_NELE);
+    return PYNQS_EOVERFLOW;
+  }
+  return 0;
+}
+
+int pynqs_num_sd(int sorb, int noA, int noB, int64_t *nsd) {
+  if (int rc = check_geometry(sorb, 0, noA, noB)) return rc;
+  long long v;
+  int rc = num_sd_checked(sorb, noA, noB, &v);
+  *nsd = v;
+  return rc;
+}
+
+int pynqs_tensor_to_onv(const uint8_t *states, int64_t n, int sorb, uint8_t *onv, void *stream) {
+  if (sorb <= 0 || sorb > PYNQS_MAX_SORB || n < 0) {
+    set_error("tensor_to_onv: bad sorb = %d or n = %lld", sorb, (long long)n);
+    return PYNQS_EVALUE;
+  }
+  return launch_tensor_to_onv(states, onv, n, sorb, (cudaStream_t)stream);
+}
+
+int pynqs_onv_to_tensor(const uint8_t *onv, int64_t n, int sorb, void *out, int dtype, void *stream) {
+  if (sorb <= 0 || sorb > PYNQS_MAX_SORB || n < 0 || (dtype != PYNQS_F32 && dtype != PYNQS_F64)) {
+    set_error("onv_to_tensor: bad sorb = %d, n = %lld or dtype = %d", sorb, (long long)n, dtype);
+    return PYNQS_EVALUE;
+  }
+  return launch_onv_to_tensor(reinterpret_cast<const u64 *>(onv), out, dtype, n, sorb, (cudaStream_t)stream);
+}
+
+int pynqs_comb(const uint8_t *bra, int64_t n, int sorb, int noA, int noB, uint8_t *comb, double *states, void *stream) {
+  if (int rc = check_geometry(sorb, 0, noA, noB)) return rc;
+  long long nsd;
+  if (int rc = num_sd_checked(sorb, noA, noB, &nsd)) return rc;
+  if (n <= 0) return 0;
+  const ExcGeom g = make_geom(sorb, noA + noB, noA, noB);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (int rc = launch_comb(reinterpret_cast<const u64 *>(bra), reinterpret_cast<u64 *>(comb), n, g, st)) return rc;
+  if (states) return launch_states(reinterpret_cast<const u64 *>(comb), states, n * (nsd + 1), sorb, st);
+  return 0;
+}
+
+int pynqs_comb_hij_fused(const uint8_t *bra, const void *h1e, const void *h2e, int64_t n, int sorb, int nele, int noA,
+                         int noB, uint8_t *comb, void *hmat, int dtype, void *stream) {
+  if (int rc = check_geometry(sorb, nele, noA, noB)) return rc;
+  long long nsd;
+  if (int rc = num_sd_checked(sorb, noA, noB, &nsd)) return rc;
+  if (dtype != PYNQS_F32 && dtype != PYNQS_F64) {
+    set_error("comb_hij_fused: dtype %d is neither float32 nor float64", dtype);
+    return PYNQS_EVALUE;
+  }
+  if (n <= 0) return 0;
+  const ExcGeom g = make_geom(sorb, nele, noA, noB);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == PYNQS_F64)
+    return launch_comb_hij_f64(reinterpret_cast<const u64 *>(bra), (const double *)h1e, (const double *)h2e,
+                               reinterpret_cast<u64 *>(comb), (double *)hmat, n, g, st);
+  return launch_comb_hij_f32(reinterpret_cast<const u64 *>(bra), (const float *)h1e, (const float *)h2e,
+                             reinterpret_cast<u64 *>(comb), (float *)hmat, n, g, st);
+}
+
+int pynqs_hij(const uint8_t *bra, const uint8_t *ket, const void *h1e, const void *h2e, int64_t n, int64_t m, int ket3d,
+              int sorb, int nele, void *out, int dtype, void *stream) {
+  if (int rc = check_geometry(sorb, nele, 0, 0)) return rc;
+  if (dtype != PYNQS_F32 && dtype != PYNQS_F64) {
+    set_error("hij: dtype %d is neither float32 nor float64", dtype);
+    return PYNQS_EVALUE;
+  }
+  if (n <= 0 || m <= 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == PYNQS_F64)
+    return launch_hij<double>(reinterpret_cast<const u64 *>(bra), reinterpret_cast<const u64 *>(ket), (const double *)h1e,
+                              (const double *)h2e, (double *)out, n, m, ket3d, sorb, nele, st);
+  return launch_hij<float>(reinterpret_cast<const u64 *>(bra), reinterpret_cast<const u64 *>(ket), (const float *)h1e,
+                           (const float *)h2e, (float *)out, n, m, ket3d, sorb, nele, st);
+}
+
+static int check_L(int L) {
+  if (L < 1 || L > PYNQS_MAX_SORB_LEN) {
+    set_error("ONV width %d bytes unsupported (need 8, 16 or 24)", 8 * L);
+    return PYNQS_EVALUE;
+  }
+  return 0;
+}
+
+int pynqs_lut(const uint8_t *key, int64_t N, const uint8_t *onv, int64_t n, int L, int64_t *idx, uint8_t *mask,
+              void *stream) {
+  if (int rc = check_L(L)) return rc;
+  return launch_lut_classic(reinterpret_cast<const u64 *>(key), N, reinterpret_cast<const u64 *>(onv), n, L,
+                            reinterpret_cast<long long *>(idx), mask, (cudaStream_t)stream);
+}
+
+int pynqs_hash_bytes(int64_t N, int L, int64_t *bytes) {
+  if (int rc = check_L(L)) return rc;
+  if (N < 0 || N >= (1LL << 32)) {
+    set_error("hash index supports 0 <= N < 2^32 keys (got %lld)", (long long)N);
+    return PYNQS_EVALUE;
+  }
+  *bytes = hash_workspace_bytes(N);
+  return 0;
+}
+
+int pynqs_hash_build(const uint8_t *key, int64_t N, int L, void *hash_ws, int64_t hash_bytes, void *stream) {
+  if (int rc = check_L(L)) return rc;
+  return launch_hash_build(reinterpret_cast<const u64 *>(key), N, L, hash_ws, hash_bytes, (cudaStream_t)stream);
+}
+
+int pynqs_lut_hashed(const uint8_t *key, int64_t N, const uint8_t *onv, int64_t n, int L, const void *hash_ws,
+                     int64_t *idx, uint8_t *mask, void *stream) {
+  if (int rc = check_L(L)) return rc;
+  return launch_lut_hashed(reinterpret_cast<const u64 *>(key), N, reinterpret_cast<const u64 *>(onv), n, L, hash_ws,
+                           reinterpret_cast<long long *>(idx), mask, (cudaStream_t)stream);
+}
+
+int pynqs_eloc_scratch_bytes(int64_t n, int sorb, int noA, int noB, int psi_complex, int64_t *bytes) {
+  if (int rc = check_geometry(sorb, 0, noA, noB)) return rc;
+  long long nsd;
+  if (int rc = num_sd_checked(sorb, noA, noB, &nsd)) return rc;
+  *bytes = eloc_scratch_bytes(n, (int)nsd, psi_complex);
+  return 0;
+}
+
+int pynqs_eloc_sample_space(const uint8_t *bra, int64_t n, const double *h1e, const double *h2e, int sorb, int nele,
+                            int noA, int noB, const uint8_t *key, const void *psi, int psi_complex, int64_t N,
+                            const void *hash_ws, void *scratch, int64_t scratch_bytes, void *eloc, void *psi0,
+                            void *stream) {
+  if (int rc = check_geometry(sorb, nele, noA, noB)) return rc;
+  long long nsd;
+  if (int rc = num_sd_checked(sorb, noA, noB, &nsd)) return rc;
+  const ExcGeom g = make_geom(sorb, nele, noA, noB);
+  return launch_eloc(reinterpret_cast<const u64 *>(bra), n, h1e, h2e, reinterpret_cast<const u64 *>(key),
+                     (const double *)psi, psi_complex, N, hash_ws, scratch, scratch_bytes, (double *)eloc, (double *)psi0, g,
+                     (cudaStream_t)stream);
+}
+
+}  // extern "C"

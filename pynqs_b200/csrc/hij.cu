@@ -1,0 +1,98 @@
+// hij.cu -- <bra|H|ket> between explicit determinant lists (get_hij_torch).
+//
+// Replaces K3/K4 (get_Hij_kernel_3D / _2D, cuda/kernel.cu:72-128): the excitation is re-derived
+// from the two bit strings (diff_type onstate.cpp:10-20, diff_orb :34-55, dispatch
+// hamiltonian.cpp:87-102).  The reference tiles 32x32 with the sample index fastest, which
+// makes adjacent threads stride M*L words; here the ket index is fastest so a warp reads
+// consecutive ket rows and writes consecutive outputs.
+#include "common.cuh"
+
+namespace pynqs {
+
+// highest set bit over all words, removing it
+template <int L>
+__device__ __forceinline__ int pop_highest(Onv<L> &d) {
+#pragma unroll
+  for (int i = L - 1; i >= 0; --i) {
+    if (d.w[i]) {
+      const int b = 63 - __clzll((long long)d.w[i]);
+      d.w[i] ^= 1ull << b;
+      return 64 * i + b;
+    }
+  }
+  return 0;
+}
+
+template <int L, typename T>
+__device__ __forceinline__ T rederived_element(const Onv<L> &x, const Onv<L> &y, const T *__restrict__ h1e,
+                                               const T *__restrict__ h2e, int sorb, int nele) {
+  Onv<L> cre, ann;  // bra-only / ket-only orbitals
+  int nc = 0, na = 0;
+#pragma unroll
+  for (int i = 0; i < L; ++i) {
+    const u64 d = x.w[i] ^ y.w[i];
+    cre.w[i] = d & x.w[i];
+    ann.w[i] = d & y.w[i];
+    nc += __popcll(cre.w[i]);
+    na += __popcll(ann.w[i]);
+  }
+  if (nc == 0 && na == 0) return diag_element<L, T>(x, h1e, h2e, sorb, nele);
+  Exc e;
+  if (nc == 1 && na == 1) {
+    const int h = pop_highest<L>(cre), p = pop_highest<L>(ann);
+    e.h0 = h | ((count_below<L>(x, h) & 1) << 8);
+    e.p0 = p | ((count_below<L>(x, p) & 1) << 8);
+    e.h1 = e.p1 = 0;
+    e.dbl = false;
+    return exc_element<L, T>(x, e, h1e, h2e, sorb);
+  }
+  if (nc == 2 && na == 2) {
+    const int h0 = pop_highest<L>(cre), h1 = pop_highest<L>(cre);
+    const int p0 = pop_highest<L>(ann), p1 = pop_highest<L>(ann);
+    e.h0 = h0 | ((count_below<L>(x, h0) & 1) << 8);
+    e.h1 = h1 | ((count_below<L>(x, h1) & 1) << 8);
+    e.p0 = p0 | ((count_below<L>(x, p0) & 1) << 8);
+    e.p1 = p1 | ((count_below<L>(x, p1) & 1) << 8);
+    e.dbl = true;
+    return exc_element<L, T>(x, e, h1e, h2e, sorb);
+  }
+  return (T)0.0;
+}
+
+template <int L, typename T>
+__global__ void __launch_bounds__(256)
+hij_kernel(const u64 *__restrict__ bra, const u64 *__restrict__ ket, const T *__restrict__ h1e, const T *__restrict__ h2e,
+           T *__restrict__ out, long long n, long long m, int ket3d, int sorb, int nele) {
+  const long long total = n * m;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const long long i = t / m, j = t - i * m;
+    const Onv<L> x = load_onv<L>(bra + i * L);
+    const Onv<L> y = load_onv<L>(ket + (ket3d ? t : j) * L);
+    out[t] = rederived_element<L, T>(x, y, h1e, h2e, sorb, nele);
+  }
+}
+
+template <typename T>
+int launch_hij(const u64 *bra, const u64 *ket, const T *h1e, const T *h2e, T *out, long long n, long long m, int ket3d,
+               int sorb, int nele, cudaStream_t st) {
+  const int L = (sorb - 1) / 64 + 1;
+  const long long total = n * m;
+  if (total == 0) return 0;
+  long long want = (total + 255) / 256;
+  const unsigned blocks = (unsigned)(want < 148LL * 64 ? want : 148LL * 64);
+  switch (L) {
+    case 1: hij_kernel<1, T><<<blocks, 256, 0, st>>>(bra, ket, h1e, h2e, out, n, m, ket3d, sorb, nele); break;
+    case 2: hij_kernel<2, T><<<blocks, 256, 0, st>>>(bra, ket, h1e, h2e, out, n, m, ket3d, sorb, nele); break;
+    case 3: hij_kernel<3, T><<<blocks, 256, 0, st>>>(bra, ket, h1e, h2e, out, n, m, ket3d, sorb, nele); break;
+    default: set_error("unsupported ONV length L=%d", L); return 1;
+  }
+  count_launch();
+  return check_launch("hij_kernel");
+}
+
+template int launch_hij<double>(const u64 *, const u64 *, const double *, const double *, double *, long long, long long,
+                                int, int, int, cudaStream_t);
+template int launch_hij<float>(const u64 *, const u64 *, const float *, const float *, float *, long long, long long, int,
+                               int, int, cudaStream_t);
+
+}  // namespace pynqs
