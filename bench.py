@@ -1,0 +1,402 @@
+#!/usr/bin/env python
+"""bench.py -- E_loc samples/sec on the Fe2S2-shaped workload (BASELINE.json configs[1]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
+    python bench.py --impl reference [...]                          # reference CPU build (oracle/_ref)
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+Workload: 40 spin orbitals, 15 alpha + 15 beta electrons (M = 7876 connected determinants per
+sample), 10^6 unique seeded random ONVs that are both the evaluated samples and the lookup
+table, random 8-fold-symmetric integrals (seed 7), psi = randn (seed 1235), FP64.
+
+One step = one pass of the hot path over the whole sample set:
+  [N > 1: NCCL all-gather of every rank's unique ONVs + psi] -> sorted table + hash index ->
+  one-pass sample-space E_loc on this rank's slice -> fused energy statistics (one collective).
+Strong scaling: the 10^6 samples are sharded over the ranks.  `value` = samples / step time with
+everything resident in HBM; `e2e` repeats the step from pinned HOST buffers (H2D of ONVs + psi,
+D2H of E_loc + statistics inside the timed region).  L2 is flushed between timed steps.
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+SORB, NOA, NOB = 40, 15, 15
+NELE = NOA + NOB
+METRIC = "E_loc samples/sec (Fe2S2 40 sorb)"
+UNIT = "samples/s"
+
+
+def algorithmic_bytes_per_sample(M: int, L: int, psi_bytes: int = 8) -> int:
+    """API path (fused + lut) B = 8L + M (16L + 17) + P_psi."""
+    return 8 * L + M * (16 * L + 17) + psi_bytes
+
+
+def hbm_peak_gbs():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def make_inputs(n_samples: int):
+    from pynqs_b200 import synthetic as S
+
+    keys = S.random_onvs(n_samples, SORB, NOA, NOB, seed=1234)
+    psi = S.random_psi(keys.shape[0], seed=1235)
+    h1e, h2e = S.random_packed_integrals(SORB, seed=7, symmetric=True)
+    return keys, psi, h1e, h2e
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.idx)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+def reference_ops():
+    """(module, kind): the unmodified reference extension if oracle/_ref was built, else the oracle port."""
+    from oracle import build_ref
+
+    if build_ref.available(1):
+        return build_ref.load_ref(1), "reference"
+    return None, "port"
+
+
+def cpu_eloc_step(ref, kind, x_np, h1e_np, h2e_np, skeys_np, spsi_np):
+    """Reference op sequence of vmc/energy/eloc.py:369-397 on the host. Returns eloc (numpy)."""
+    import torch
+
+    if kind == "reference":
+        x, h1e, h2e = torch.from_numpy(x_np), torch.from_numpy(h1e_np), torch.from_numpy(h2e_np)
+        key, val = torch.from_numpy(skeys_np), torch.from_numpy(spsi_np)
+        comb_x, comb_hij = ref.get_comb_hij_fused(x, h1e, h2e, SORB, NELE, NOA, NOB)
+        x1 = comb_x.reshape(-1, comb_x.size(2))
+        psi_x1 = torch.zeros(x.size(0), comb_x.size(1), dtype=val.dtype)
+        idx_array, mask = ref.wavefunction_lut(key, x1, SORB)
+        baseline = torch.arange(x1.size(0), dtype=torch.int64)
+        psi_x1.view(-1)[baseline[mask]] = val[idx_array.masked_select(mask)]
+        return ((psi_x1.T / psi_x1[..., 0]).T * comb_hij).sum(-1).numpy()
+    from oracle import oracle as O
+
+    return O.eloc_sample_space(x_np, h1e_np, h2e_np, skeys_np, spsi_np, SORB, NELE, NOA, NOB)
+
+
+def time_cpu_baseline(keys, psi, h1e, h2e, budget_s=12.0, chunk=512):
+    """Bounded sample of the same workload on the host cores: E_loc of `m` samples against the full table."""
+    import torch
+
+    from oracle import oracle as O
+
+    ref, kind = reference_ops()
+    cores = os.cpu_count() if kind == "reference" else 1
+    torch.set_num_threads(cores)
+    order = O.sort_onv(keys)
+    skeys, spsi = np.ascontiguousarray(keys[order]), np.ascontiguousarray(psi[order])
+    if kind == "port":
+        chunk = 32
+    cpu_eloc_step(ref, kind, keys[:chunk], h1e, h2e, skeys, spsi)  # warm-up
+    done, t0 = 0, time.perf_counter()
+    while True:
+        cpu_eloc_step(ref, kind, keys[done : done + chunk], h1e, h2e, skeys, spsi)
+        done += chunk
+        el = time.perf_counter() - t0
+        if el > budget_s or done + chunk > keys.shape[0]:
+            break
+    return {"value": done / el, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": f"{done} of {keys.shape[0]} samples in {chunk}-sample chunks against the full {keys.shape[0]}-key table "
+                      f"(get_comb_hij_fused + wavefunction_lut + torch reduce), {el:.1f} s"}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+
+    from oracle import oracle as O
+
+    keys, psi, h1e, h2e = make_inputs(args.samples)
+    ref, kind = reference_ops()
+    cores = os.cpu_count() if kind == "reference" else 1
+    torch.set_num_threads(cores)
+    order = O.sort_onv(keys)
+    skeys, spsi = np.ascontiguousarray(keys[order]), np.ascontiguousarray(psi[order])
+    per_step = args.ref_samples if kind == "reference" else 64
+    chunk = 512 if kind == "reference" else 32
+    M = 7876
+
+    def step(i):
+        lo = (i * per_step) % (keys.shape[0] - per_step)
+        for b in range(lo, lo + per_step, chunk):
+            cpu_eloc_step(ref, kind, keys[b : min(b + chunk, lo + per_step)], h1e, h2e, skeys, spsi)
+
+    for i in range(args.warmup):
+        step(i)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step(args.warmup + i)
+    el = time.perf_counter() - t0
+    value = per_step * args.steps / el
+    sample = (f"each step = E_loc of {per_step} samples ({chunk}-sample chunks) against the prebuilt sorted "
+              f"{keys.shape[0]}-key table; table sort not timed")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "fe2s2_cas30e20o_40sorb_15a15b", "sorb": SORB, "noA": NOA, "noB": NOB, "M": M,
+                   "n_samples": int(keys.shape[0]), "lut_keys": int(keys.shape[0]), "integrals": "random 8-fold symmetric, seed 7"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the product has no CPU path); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    from pynqs_b200 import _lib
+    from pynqs_b200 import C_extension as ops
+    from pynqs_b200.distributed import energy_statistics, exchange_unique_samples, rank_slice
+    from pynqs_b200.lut import WavefunctionLUT, split_length_idx
+
+    _lib.load()
+    keys_np, psi_np, h1e_np, h2e_np = make_inputs(args.samples)
+    n_total = keys_np.shape[0]
+    M = ops.get_Num_SinglesDoubles(SORB, NOA, NOB) + 1
+    # every rank "samples" a contiguous piece of the unique set (disjoint pieces, like use_same_tree)
+    cuts = [0] + split_length_idx(n_total, world)
+    lo, hi = cuts[rank], cuts[rank + 1]
+    host_keys = torch.from_numpy(keys_np[lo:hi]).pin_memory()
+    host_psi = torch.from_numpy(psi_np[lo:hi]).pin_memory()
+    d_keys, d_psi = host_keys.to(dev), host_psi.to(dev)
+    h1e, h2e = torch.from_numpy(h1e_np).to(dev), torch.from_numpy(h2e_np).to(dev)
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+    host_eloc = torch.empty(hi - lo + 1, dtype=torch.float64).pin_memory()
+
+    kern_ms = []
+
+    def step(from_host: bool):
+        if from_host:
+            k = host_keys.to(dev, non_blocking=True)
+            p = host_psi.to(dev, non_blocking=True)
+        else:
+            k, p = d_keys, d_psi
+        uniq, wf, cnt = exchange_unique_samples(k, p, None, disjoint=True)
+        lut = WavefunctionLUT(uniq, wf, SORB, dev, rank=rank, world_size=world)
+        b, e = rank_slice(uniq.size(0), rank, world)
+        x = uniq[b:e]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        eloc, psi0 = ops.eloc_sample_space(x, h1e, h2e, SORB, NELE, NOA, NOB, lut.bra_key, lut.wf_value, lut.hash_index)
+        e1.record()
+        prob = psi0 * psi0 / (lut.wf_value * lut.wf_value).sum() * world  # reference convention: prob * world_size
+        st = energy_statistics(eloc, prob)
+        if from_host:
+            host_eloc[: e - b].copy_(eloc, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        kern_ms.append((e0, e1, e - b))
+        return st
+
+    def timed(n_steps: int, from_host: bool):
+        total_ms = 0.0
+        for _ in range(n_steps):
+            flush.fill_(1)  # write > L2 (126 MB) between timed steps
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            s, t = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            st = step(from_host)
+            t.record()
+            torch.cuda.synchronize()
+            total_ms += s.elapsed_time(t)
+        tt = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item()), st
+
+    for _ in range(args.warmup):
+        step(False)
+    torch.cuda.synchronize()
+    kern_ms.clear()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = _lib.launch_count()
+    total_ms, st = timed(args.steps, False)
+    launches = _lib.launch_count() - l0
+    kern = [(a.elapsed_time(b), n) for a, b, n in kern_ms]
+    e2e_ms, st2 = timed(args.steps, True)
+    clocks = sampler.stop() if rank == 0 else None
+
+    ms_per_step = total_ms / args.steps
+    value = n_total / (ms_per_step * 1e-3)
+    e2e_value = n_total / (e2e_ms / args.steps * 1e-3)
+    B = algorithmic_bytes_per_sample(M, 1)
+    k_ms = sum(t for t, _ in kern) / len(kern)
+    k_n = kern[0][1]
+    peak, peak_src = hbm_peak_gbs()
+    achieved = B * k_n / (k_ms * 1e-3) / 1e9
+    roof = {"bound": "hbm", "kernel": "eloc_kernel<1,real> (+diag_kernel)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+            "algorithmic_bytes_per_sample": B, "samples_per_launch": k_n, "kernel_ms": k_ms,
+            "note": "one-pass kernel: algorithmic bytes are the API-path (fused+lut) bytes it replaces, SURVEY.md 8(d); "
+                    "its real DRAM traffic is ~16 B/sample, see profiles/"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": "fe2s2_cas30e20o_40sorb_15a15b", "sorb": SORB, "noA": NOA, "noB": NOB, "M": M, "n_samples": n_total,
+                   "lut_keys": n_total, "integrals": "random 8-fold symmetric, seed 7", "method": "sample-space, one-pass kernel",
+                   "l2": "flushed between timed steps (512 MiB write)", "parallelism": f"samples sharded over {world} rank(s)",
+                   "step": "exchange + table sort + hash index + E_loc + statistics"},
+        "roofline": roof,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n_total * 16), "d2h_bytes_per_step": int(n_total * 8 + 40 * world),
+                "ms_per_step": e2e_ms / args.steps},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "energy": {"mean": st["mean"], "var": st["var"], "mean_e2e": st2["mean"]},
+    }
+    if world == 1 and not args.no_api_path:
+        line["api_path"] = time_api_path(ops, dev, d_keys, d_psi, h1e, h2e, M, peak)
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = time_cpu_baseline(keys_np, psi_np, h1e_np, h2e_np)
+    else:
+        line["cpu_baseline"] = None
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def time_api_path(ops, dev, d_keys, d_psi, h1e, h2e, M, peak, chunk=32768, reps=5):
+    """The materialising reference-API kernels on one chunk: real HBM writers, reported beside the headline."""
+    import torch
+
+    from pynqs_b200.lut import WavefunctionLUT
+
+    lut = WavefunctionLUT(d_keys, d_psi, SORB, dev, rank=0, world_size=1)
+    x = lut.bra_key[:chunk]
+
+    def t(fn):
+        for _ in range(2):
+            out = fn()
+        ts = []
+        for _ in range(reps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            out = fn()
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        return statistics.median(ts), out
+
+    f_ms, (comb, hmat) = t(lambda: ops.get_comb_hij_fused(x, h1e, h2e, SORB, NELE, NOA, NOB))
+    flat = comb.view(-1, 8)
+    l_ms, _ = t(lambda: ops.wavefunction_lut(lut.bra_key, flat, SORB, hash_index=lut.hash_index))
+    fb, lb = (16 * M + 8) * chunk, 17 * M * chunk
+    return {
+        "chunk_samples": chunk,
+        "get_comb_hij_fused": {"ms": f_ms, "samples_per_s": chunk / f_ms * 1e3, "GBps": fb / f_ms / 1e6, "frac_hbm": fb / f_ms / 1e6 / peak},
+        "wavefunction_lut": {"ms": l_ms, "samples_per_s": chunk / l_ms * 1e3, "GBps": lb / l_ms / 1e6, "frac_hbm": lb / l_ms / 1e6 / peak},
+        "note": "includes torch output allocation; outputs (comb 2.06 GB + Hmat 2.06 GB per chunk) exceed L2",
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--samples", type=int, default=1_000_000)
+    ap.add_argument("--ref-samples", type=int, default=4096, help="samples per step of the reference CPU arm")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-api-path", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -55,8 +55,9 @@ def exchange_unique_samples(onv: Tensor, psi: Tensor, counts: Optional[Tensor] =
         rec[:n_r, :w] = onv
         rec[:n_r, w : w + pw] = psi_bytes.view(n_r, pw)
         rec[:n_r, w + pw :] = counts.to(torch.int64).contiguous().view(torch.uint8).view(n_r, 8)
-        gathered = torch.empty((world, n_max, rec_w), dtype=torch.uint8, device=dev)
+        gathered = torch.empty((world * n_max, rec_w), dtype=torch.uint8, device=dev)
         dist.all_gather_into_tensor(gathered, rec)
+        gathered = gathered.view(world, n_max, rec_w)
         parts = [gathered[r, : n_list[r]] for r in range(world)]
         cat = torch.cat(parts)
         all_onv = cat[:, :w].contiguous()
@@ -68,8 +69,6 @@ def exchange_unique_samples(onv: Tensor, psi: Tensor, counts: Optional[Tensor] =
         return all_onv, all_psi, all_cnt
     uniq, inv = torch.unique(all_onv, dim=0, return_inverse=True)
     m = uniq.size(0)
-    if m == all_onv.size(0) and world == 1:
-        pass
     first = torch.full((m,), all_onv.size(0), dtype=torch.int64, device=dev)
     first.scatter_reduce_(0, inv, torch.arange(all_onv.size(0), device=dev), reduce="amin")
     merged_cnt = torch.zeros(m, dtype=torch.int64, device=dev).index_add_(0, inv, all_cnt)
@@ -113,8 +112,9 @@ def energy_statistics(eloc: Tensor, prob: Tensor, counts: Optional[int] = None) 
     mu_im = mu.imag if cplx else torch.zeros_like(mu_re)
     vec = torch.stack([w, mu_re * 1.0, mu_im * 1.0, m2, torch.tensor(float(e.numel()), dtype=torch.float64, device=e.device)])
     if world > 1:
-        allv = torch.empty((world, 5), dtype=torch.float64, device=vec.device)
+        allv = torch.empty(world * 5, dtype=torch.float64, device=vec.device)
         dist.all_gather_into_tensor(allv, vec)
+        allv = allv.view(world, 5)
     else:
         allv = vec.view(1, 5)
     allv = allv.cpu()

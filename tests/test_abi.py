@@ -1,0 +1,83 @@
+"""The C-ABI library loads without a GPU and exports exactly what include/pynqs_b200.h declares."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from pynqs_b200 import _lib, build
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    build.build()
+    return _lib.load()
+
+
+def header_symbols():
+    txt = open(os.path.join(ROOT, "include", "pynqs_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(pynqs_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_header_and_loader_agree():
+    assert header_symbols() == sorted(_lib.SYMBOLS)
+
+
+def test_every_declared_symbol_is_exported(lib):
+    for s in header_symbols():
+        assert hasattr(lib, s), s
+
+
+def test_host_only_entry_points(lib):
+    assert lib.pynqs_abi_version() == 1
+    out = ctypes.c_int64()
+    assert lib.pynqs_num_sd(40, 15, 15, ctypes.byref(out)) == 0 and out.value == 7875   # Fe2S2
+    assert lib.pynqs_num_sd(12, 3, 3, ctypes.byref(out)) == 0 and out.value == 117
+    assert lib.pynqs_num_sd(52, 5, 5, ctypes.byref(out)) == 0 and out.value == 15435
+    assert lib.pynqs_num_sd(100, 25, 25, ctypes.byref(out)) == 0 and out.value == 571875
+    assert lib.pynqs_check_sorb(40, 30) == 0
+    assert lib.pynqs_check_sorb(52, 10) == 0            # relaxed w.r.t. the reference
+    assert lib.pynqs_check_sorb(193, 10) == _lib.EVALUE
+    assert lib.pynqs_check_sorb(64, 121) == _lib.EOVERFLOW
+    assert b"nele" in lib.pynqs_last_error()
+    nb = ctypes.c_int64()
+    assert lib.pynqs_hash_bytes(ctypes.c_int64(1000000), 1, ctypes.byref(nb)) == 0 and nb.value == 256 + 32 * (1 << 20)
+    assert lib.pynqs_hash_bytes(ctypes.c_int64(10), 4, ctypes.byref(nb)) == _lib.EVALUE
+
+
+def test_error_mapping():
+    from pynqs_b200 import C_extension as ops
+
+    with pytest.raises(ValueError):
+        ops.check_sorb(200, 10)
+    with pytest.raises(OverflowError):
+        ops.check_sorb(64, 200)
+    ops.check_sorb(40, 30)
+    assert ops.get_Num_SinglesDoubles(40, 15, 15) == 7875
+    assert (ops.MAX_SORB, ops.MAX_SORB_LEN, ops.MAX_NELE) == (192, 3, 120)
+
+
+def test_cpu_tensors_are_refused_loudly():
+    import torch
+
+    from pynqs_b200 import C_extension as ops
+
+    bra = torch.zeros((1, 8), dtype=torch.uint8)
+    with pytest.raises(RuntimeError, match="CUDA-only"):
+        ops.get_comb_tensor(bra, 4, 2, 1, 1)
+    with pytest.raises(RuntimeError, match="CUDA-only"):
+        ops.wavefunction_lut(bra, bra, 4)
+    with pytest.raises(NotImplementedError):
+        ops.spin_flip_rand(bra, 4, 2, 1, 1, 0)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "pynqs_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in txt.replace("# oracle", ""), f"{f} mentions the oracle"

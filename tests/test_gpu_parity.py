@@ -1,0 +1,305 @@
+"""Parity of the CUDA path (through the C ABI, via pynqs_b200.C_extension) against
+  * the reference goldens in tests/golden/ (outputs of the unmodified reference), and
+  * the CPU oracle on the same seeded inputs.
+Bars: determinant lists / lookup indices bit-exact; H_ij bit-exact where the summation order is
+the reference's (asserted via SHA-256 of the raw bytes), and never worse than 1e-12 relative;
+E_loc 1e-12 relative; mean energy 1e-10 Ha."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as O
+from pynqs_b200 import C_extension as ops
+from pynqs_b200 import synthetic as S
+from pynqs_b200.energy import local_energy_sample_space, local_energy_three_call
+from pynqs_b200.lut import WavefunctionLUT, sort_onv
+
+from util import OPS_CASES, fe2s2, load, ops_inputs, sha
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _library_loaded():
+    from pynqs_b200 import _lib
+
+    _lib.load()  # fails loudly if libpynqs_b200.so is missing: there is no fallback
+    assert torch.cuda.is_available()
+
+
+# ---- operators against the reference goldens -----------------------------------------------------
+@pytest.mark.parametrize("name", OPS_CASES)
+def test_comb_hij_fused_matches_reference(name):
+    c = ops_inputs(name)
+    g = c["g"]
+    comb, hmat = ops.get_comb_hij_fused(dev(c["bra"]), dev(c["h1e"]), dev(c["h2e"]), c["sorb"], c["nele"], c["noA"], c["noB"])
+    comb, hmat = comb.cpu().numpy(), hmat.cpu().numpy()
+    k = g["comb_rows"].shape[0]
+    np.testing.assert_array_equal(comb[:k, :: c["stride"]], g["comb_rows"])
+    np.testing.assert_allclose(hmat[:k, :: c["stride"]], g["hmat_rows"], rtol=1e-12 if hmat.dtype == np.float64 else 1e-6, atol=0)
+    assert sha(comb) == str(g["comb_sha"])      # connected determinants bit-exact
+    assert sha(hmat) == str(g["hmat_sha"])      # H_ij bit-exact
+
+
+@pytest.mark.parametrize("name", OPS_CASES)
+def test_get_comb_tensor_matches_reference(name):
+    c = ops_inputs(name)
+    comb, second = ops.get_comb_tensor(dev(c["bra"]), c["sorb"], c["nele"], c["noA"], c["noB"], False)
+    assert sha(comb.cpu().numpy()) == str(c["g"]["comb_sha"])
+    assert second.device.type == "cpu" and second.dtype == torch.float64 and second.tolist() == [1.0]
+
+
+def test_get_comb_tensor_flag_bit_states():
+    c = ops_inputs("ops_odd_14sorb_4a2b")
+    comb, states = ops.get_comb_tensor(dev(c["bra"][:7]), c["sorb"], c["nele"], c["noA"], c["noB"], True)
+    want = O.onv_to_tensor(comb.cpu().numpy().reshape(-1, 8), c["sorb"]).reshape(7, -1, c["sorb"])
+    np.testing.assert_array_equal(states.cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("name", OPS_CASES)
+def test_get_hij_torch_3d_equals_fused_and_2d_matches_reference(name):
+    c = ops_inputs(name)
+    g = c["g"]
+    bra, h1e, h2e = dev(c["bra"]), dev(c["h1e"]), dev(c["h2e"])
+    comb, hmat = ops.get_comb_hij_fused(bra, h1e, h2e, c["sorb"], c["nele"], c["noA"], c["noB"])
+    h3 = ops.get_hij_torch(bra, comb, h1e, h2e, c["sorb"], c["nele"])
+    assert torch.equal(h3, hmat)
+    m2 = g["hij2d"].shape[0]
+    h2 = ops.get_hij_torch(bra[:m2], bra[:m2].clone(), h1e, h2e, c["sorb"], c["nele"])
+    np.testing.assert_array_equal(h2.cpu().numpy(), g["hij2d"])
+
+
+def test_fe2s2_real_integrals_match_reference():
+    f = fe2s2()
+    g = load("ops_c2_fe2s2")
+    n = int(g["n"])
+    comb, hmat = ops.get_comb_hij_fused(dev(f["ci"][:n]), dev(f["h1e"]), dev(f["h2e"]), f["sorb"], f["nele"], f["noA"], f["noB"])
+    assert tuple(comb.shape) == (n, 7876, 8)
+    np.testing.assert_array_equal(hmat[:4].cpu().numpy(), g["hmat_rows"])
+    assert sha(comb.cpu().numpy()) == str(g["comb_sha"]) and sha(hmat.cpu().numpy()) == str(g["hmat_sha"])
+
+
+def test_pyi_known_answers_on_device():
+    st = torch.tensor([1, 1, 1, 1, 0, 0, 0, 0], dtype=torch.uint8, device=DEV)
+    assert ops.tensor_to_onv(st, 8).cpu().tolist() == [[0b1111, 0, 0, 0, 0, 0, 0, 0]]
+    onv = torch.tensor([0b1111, 0, 0, 0, 0, 0, 0, 0], dtype=torch.uint8, device=DEV)
+    old = torch.get_default_dtype()
+    try:
+        torch.set_default_dtype(torch.float64)
+        out = ops.onv_to_tensor(onv, 8)
+        assert out.dtype == torch.float64 and out.cpu().tolist() == [[1, 1, 1, 1, -1, -1, -1, -1]]
+        torch.set_default_dtype(torch.float32)
+        assert ops.onv_to_tensor(onv, 8).dtype == torch.float32  # follows the default dtype (cpu_tensor.cpp:55)
+    finally:
+        torch.set_default_dtype(old)
+    bra = torch.tensor([[0b1100, 0, 0, 0, 0, 0, 0, 0]], dtype=torch.uint8, device=DEV)
+    comb, states = ops.get_comb_tensor(bra, 4, 2, 1, 1, True)
+    assert comb[0, :, 0].cpu().tolist() == [12, 9, 6, 3]
+    assert states[0].cpu().tolist() == [[-1, -1, 1, 1], [1, -1, -1, 1], [-1, 1, 1, -1], [1, 1, -1, -1]]
+    key = np.zeros((6, 8), dtype=np.uint8)
+    key[:, :2] = [[3, 0], [6, 0], [12, 0], [9, 1], [9, 2], [1, 3]]
+    q = np.zeros((6, 8), dtype=np.uint8)
+    q[:, :2] = [[12, 0], [9, 2], [6, 0], [3, 0], [14, 0], [1, 3]]
+    idx, mask = ops.wavefunction_lut(dev(key), dev(q), 4)
+    assert idx.cpu().tolist() == [2, 4, 1, 0, -1, 5] and mask.cpu().tolist() == [True, True, True, True, False, True]
+    assert idx.dtype == torch.int64 and mask.dtype == torch.bool
+
+
+def test_conversions_roundtrip_multiword():
+    for sorb in (12, 64, 100, 132, 192):
+        rng = np.random.default_rng(sorb)
+        st = (rng.random((257, sorb)) < 0.4).astype(np.uint8)
+        onv = ops.tensor_to_onv(dev(st), sorb)
+        np.testing.assert_array_equal(onv.cpu().numpy(), O.tensor_to_onv(st, sorb))
+        old = torch.get_default_dtype()
+        torch.set_default_dtype(torch.float64)
+        try:
+            z = ops.onv_to_tensor(onv, sorb).cpu().numpy()
+        finally:
+            torch.set_default_dtype(old)
+        np.testing.assert_array_equal(z, 2.0 * st - 1.0)
+
+
+# ---- lookup ----------------------------------------------------------------------------------------
+@pytest.mark.parametrize("L,sorb,na", [(1, 40, 15), (2, 100, 25), (3, 132, 3)])
+def test_lookup_classic_and_hashed_equal_oracle(L, sorb, na):
+    keys = S.random_onvs(20000 if L < 3 else 3000, sorb, na, na, seed=60 + L)
+    order = O.sort_onv(keys)
+    skeys = keys[order]
+    rng = np.random.default_rng(61)
+    q = np.concatenate([keys[rng.permutation(len(keys))[:5000]], S.random_onvs(5000, sorb, na, na, seed=62 + L)])
+    want_idx, want_mask = O.lut(skeys, q)
+    dk, dq = dev(skeys), dev(q)
+    idx, mask = ops.wavefunction_lut(dk, dq, sorb)                                  # classic search
+    np.testing.assert_array_equal(idx.cpu().numpy(), want_idx)
+    np.testing.assert_array_equal(mask.cpu().numpy(), want_mask)
+    idx2, mask2 = ops.wavefunction_lut(dk, dq, sorb, hash_index=ops.HashIndex(dk))  # hash index
+    np.testing.assert_array_equal(idx2.cpu().numpy(), want_idx)
+    np.testing.assert_array_equal(mask2.cpu().numpy(), want_mask)
+    # device sort == reference order
+    np.testing.assert_array_equal(sort_onv(dev(keys)).cpu().numpy(), order)
+
+
+def test_lookup_golden_through_lut_mirror():
+    g = load("lut_lookup_l1")
+    rng = np.random.default_rng(31)
+    keys = S.random_onvs(5000, 40, 15, 15, seed=32)
+    psi = S.random_psi(5000, seed=33)
+    lut = WavefunctionLUT(dev(keys), dev(psi), 40, DEV, rank=0, world_size=1)
+    q = np.concatenate([keys[rng.permutation(5000)[:700]], S.random_onvs(700, 40, 15, 15, seed=34)])
+    hit, miss, val = lut.lookup(dev(q))
+    np.testing.assert_array_equal(hit.cpu().numpy(), g["hit"])
+    np.testing.assert_array_equal(miss.cpu().numpy(), g["miss"])
+    np.testing.assert_array_equal(val.cpu().numpy(), g["val"])
+
+
+def test_lookup_with_duplicate_keys_falls_back_to_classic_probe_sequence():
+    keys = S.random_onvs(1000, 40, 15, 15, seed=70)
+    keys = np.concatenate([keys, keys[:300], keys[:100]])
+    skeys = keys[O.sort_onv(keys)]
+    q = np.concatenate([keys[:500], S.random_onvs(200, 40, 15, 15, seed=71)])
+    want_idx, _ = O.lut(skeys, q)
+    dk = dev(skeys)
+    idx, _ = ops.wavefunction_lut(dk, dev(q), 40, hash_index=ops.HashIndex(dk))
+    np.testing.assert_array_equal(idx.cpu().numpy(), want_idx)   # same element of each duplicate run as the reference
+
+
+def test_empty_and_tiny_inputs():
+    e = torch.empty((0, 8), dtype=torch.uint8, device=DEV)
+    h1e, h2e = (dev(a) for a in S.random_packed_integrals(12, seed=1, symmetric=False))
+    comb, hmat = ops.get_comb_hij_fused(e, h1e, h2e, 12, 6, 3, 3)
+    assert tuple(comb.shape) == (0, 118, 8) and tuple(hmat.shape) == (0, 118)
+    assert tuple(ops.get_comb_tensor(e, 12, 6, 3, 3)[0].shape) == (0, 118, 8)
+    keys = dev(S.random_onvs(10, 12, 3, 3, seed=2))
+    idx, mask = ops.wavefunction_lut(keys, e, 12)
+    assert idx.numel() == 0 and mask.numel() == 0
+    assert tuple(ops.get_hij_torch(e, keys, h1e, h2e, 12, 6).shape) == (0, 10)
+    assert tuple(ops.tensor_to_onv(torch.empty((0, 12), dtype=torch.uint8, device=DEV), 12).shape) == (0, 8)
+    # a table with no keys: everything is a miss
+    idx, mask = ops.wavefunction_lut(e, keys, 12)
+    assert (idx == -1).all() and not mask.any()
+    idx, mask = ops.wavefunction_lut(e, keys, 12, hash_index=ops.HashIndex(e))
+    assert (idx == -1).all() and not mask.any()
+    with pytest.raises(ValueError):
+        ops.get_comb_tensor(keys, 100, 6, 3, 3)          # width does not match sorb
+    with pytest.raises(RuntimeError):
+        ops.get_comb_tensor(keys[:, :4].T, 12, 6, 3, 3)  # non-contiguous
+
+
+# ---- E_loc ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag,cplx", [("real", False), ("complex", True)])
+def test_eloc_matches_reference_python(tag, cplx):
+    f = fe2s2()
+    g = load(f"eloc_fe2s2_{tag}")
+    psi = S.random_psi(f["ci"].shape[0], seed=int(g["psi_seed"]), complex_=cplx)
+    lut = WavefunctionLUT(dev(f["ci"]), dev(psi), f["sorb"], DEV, rank=0, world_size=1)
+    first, n = int(g["first"]), int(g["n"])
+    x = dev(f["ci"][first : first + n])
+    h1e, h2e = dev(f["h1e"]), dev(f["h2e"])
+    dtype = torch.complex128 if cplx else torch.double
+    eloc, sloc, psi_x = local_energy_sample_space(x, h1e, h2e, lut, f["sorb"], f["nele"], f["noA"], f["noB"], dtype)
+    np.testing.assert_allclose(eloc.cpu().numpy(), g["eloc"], rtol=1e-12, atol=0)
+    np.testing.assert_array_equal(psi_x.cpu().numpy(), g["psi_x"])
+    assert not sloc.any()
+    eloc3, _, psi3 = local_energy_three_call(x, h1e, h2e, lut, f["sorb"], f["nele"], f["noA"], f["noB"], dtype, batch=24)
+    np.testing.assert_allclose(eloc3.cpu().numpy(), g["eloc"], rtol=1e-12, atol=0)
+    np.testing.assert_array_equal(psi3.cpu().numpy(), g["psi_x"])
+
+
+def test_eloc_full_space_and_rayleigh_quotient():
+    g = load("eloc_c1_fullspace")
+    keys = S.random_onvs(400, 12, 3, 3, seed=51)
+    h1e, h2e = S.random_packed_integrals(12, seed=52, symmetric=True)
+    psi = S.random_psi(400, seed=53)
+    lut = WavefunctionLUT(dev(keys), dev(psi), 12, DEV, rank=0, world_size=1)
+    eloc, _, psi_x = local_energy_sample_space(dev(keys), dev(h1e), dev(h2e), lut, 12, 6, 3, 3)
+    np.testing.assert_allclose(eloc.cpu().numpy(), g["eloc"], rtol=1e-12, atol=1e-13)
+    np.testing.assert_array_equal(psi_x.cpu().numpy(), psi)
+    H = ops.get_hij_torch(dev(keys), dev(keys), dev(h1e), dev(h2e), 12, 6).cpu().numpy()
+    np.testing.assert_array_equal(H, H.T)
+    e_dense = psi @ H @ psi / (psi @ psi)
+    e_vmc = float(np.sum(psi * psi * eloc.cpu().numpy()) / (psi @ psi))
+    assert abs(e_dense - e_vmc) < 1e-10
+
+
+def test_eloc_sample_missing_from_table_gives_nan_like_reference():
+    keys = S.random_onvs(300, 12, 3, 3, seed=80)
+    h1e, h2e = S.random_packed_integrals(12, seed=81, symmetric=True)
+    lut = WavefunctionLUT(dev(keys[:200]), dev(S.random_psi(200, seed=82)), 12, DEV, rank=0, world_size=1)
+    eloc, _, psi_x = local_energy_sample_space(dev(keys[190:210]), dev(h1e), dev(h2e), lut, 12, 6, 3, 3)
+    e = eloc.cpu().numpy()
+    assert np.isfinite(e[:10]).all() and np.isnan(e[10:]).all()       # psi(x) = 0 -> 0/0
+    assert (psi_x[10:] == 0).all()
+
+
+# ---- larger, size-independent properties ---------------------------------------------------------------
+def test_fe2s2_shape_at_scale_properties():
+    """Config-2 geometry (40 sorb, 15a15b, M = 7876) at 2e5 table keys / 8192 evaluated samples:
+    fused == rederived, hash lookup == classic search, one-pass E_loc == three-call path,
+    mean energy within 1e-10 Ha; oracle spot check."""
+    sorb, noA, noB, nele = 40, 15, 15, 30
+    N, n = 200_000, 8192
+    keys = S.random_onvs(N, sorb, noA, noB, seed=1234)
+    psi = S.random_psi(N, seed=1235)
+    h1e_np, h2e_np = S.random_packed_integrals(sorb, seed=7, symmetric=True)
+    h1e, h2e = dev(h1e_np), dev(h2e_np)
+    lut = WavefunctionLUT(dev(keys), dev(psi), sorb, DEV, rank=0, world_size=1)
+    x = dev(keys[:n])
+    comb, hmat = ops.get_comb_hij_fused(x[:2048], h1e, h2e, sorb, nele, noA, noB)
+    assert torch.equal(ops.get_hij_torch(x[:2048], comb, h1e, h2e, sorb, nele), hmat)
+    flat = comb.view(-1, 8)
+    i1, m1 = ops.wavefunction_lut(lut.bra_key, flat[: 4_000_000], sorb)                       # >= hash threshold
+    from pynqs_b200 import _lib
+
+    i2 = torch.empty_like(i1)
+    m2 = torch.empty_like(m1)
+    _lib.check(_lib.load().pynqs_lut(_lib.vp(lut.bra_key.data_ptr()), _lib.i64(N), _lib.vp(flat.data_ptr()), _lib.i64(4_000_000), 1,
+                                     _lib.vp(i2.data_ptr()), _lib.vp(m2.data_ptr()), _lib.vp(torch.cuda.current_stream().cuda_stream)))
+    assert torch.equal(i1, i2) and torch.equal(m1, m2)
+    assert int(m1.sum()) >= 508  # at least the bra rows
+    e1, _, p1 = local_energy_sample_space(x, h1e, h2e, lut, sorb, nele, noA, noB)
+    e3, _, p3 = local_energy_three_call(x, h1e, h2e, lut, sorb, nele, noA, noB, batch=2048)
+    np.testing.assert_allclose(e1.cpu().numpy(), e3.cpu().numpy(), rtol=1e-12, atol=0)
+    assert torch.equal(p1, p3) and torch.equal(p1, dev(psi[:n]))
+    prob = (p1 * p1) / (p1 * p1).sum()
+    assert abs(float((prob * e1).sum() - (prob * e3).sum())) < 1e-10
+    # oracle spot check of the one-pass kernel
+    order = O.sort_onv(keys)
+    want = O.eloc_sample_space(keys[:8], h1e_np, h2e_np, keys[order], psi[order], sorb, nele, noA, noB)
+    np.testing.assert_allclose(e1[:8].cpu().numpy(), want, rtol=1e-12, atol=0)
+
+
+def test_row_index_beyond_int32():
+    """n * M > 2^31 rows in one call (the reference's int indexing overflows here, kernel.cu:190,220)."""
+    sorb, noA, noB, nele = 40, 15, 15, 30
+    n = 273_000                      # 273000 * 7876 = 2.15e9 rows, 17.2 GB comb + 17.2 GB Hmat
+    free, _ = torch.cuda.mem_get_info()
+    if free < 48 * 2**30:
+        pytest.skip("needs ~36 GB of free device memory")
+    bra = S.random_onvs(4096, sorb, noA, noB, seed=90)
+    big = np.tile(bra, (n // 4096 + 1, 1))[:n]
+    h1e_np, h2e_np = S.random_packed_integrals(sorb, seed=7, symmetric=True)
+    comb, hmat = ops.get_comb_hij_fused(dev(big), dev(h1e_np), dev(h2e_np), sorb, nele, noA, noB)
+    want_c, want_h = O.comb_hij_fused(big[-2:], h1e_np, h2e_np, sorb, nele, noA, noB)
+    np.testing.assert_array_equal(comb[-2:].cpu().numpy(), want_c)
+    np.testing.assert_array_equal(hmat[-2:].cpu().numpy(), want_h)
+    np.testing.assert_array_equal(comb[0].cpu().numpy(), O.comb(big[:1], sorb, noA, noB)[0])
+    del comb, hmat
+    torch.cuda.empty_cache()
+
+
+def test_192_sorb_three_words_against_oracle():
+    """Config-5 geometry: 192 spin orbitals (L = 3), 4a4b, M = 186393, packed h2e = 1.345 GB."""
+    sorb, noA, noB = 192, 4, 4
+    h1e_np, h2e_np = S.random_packed_integrals(sorb, seed=5, symmetric=False)
+    assert h2e_np.size == 168_113_616
+    bra = S.random_onvs(2, sorb, noA, noB, seed=6)
+    comb, hmat = ops.get_comb_hij_fused(dev(bra), dev(h1e_np), dev(h2e_np), sorb, 8, noA, noB)
+    want_c, want_h = O.comb_hij_fused(bra, h1e_np, h2e_np, sorb, 8, noA, noB)
+    np.testing.assert_array_equal(comb.cpu().numpy(), want_c)
+    np.testing.assert_array_equal(hmat.cpu().numpy(), want_h)
