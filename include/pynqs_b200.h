@@ -72,11 +72,19 @@ int pynqs_onv_to_tensor(const uint8_t *onv, int64_t n, int sorb, void *out, int 
 int pynqs_comb(const uint8_t *bra, int64_t n, int sorb, int noA, int noB, uint8_t *comb, double *states,
                void *stream);
 
+/* Gather-friendly internal copy of the packed h2e (same numbers, bit for bit), built once per
+ * Hamiltonian into a caller-provided workspace of pynqs_prepared_bytes(sorb, dtype) bytes and
+ * passed to pynqs_comb_hij_fused.  h2e is the packed array of cpp_src/cpu/hamiltonian.cpp:13-31. */
+int pynqs_prepared_bytes(int sorb, int dtype, int64_t *bytes);
+int pynqs_prepare_integrals(const void *h2e, int sorb, int dtype, void *prep_ws, int64_t prep_bytes, void *stream);
+
 /* replaces get_comb_hij_fused (bind.cpp:239-250, cuda_tensor.cpp:162-215; kernels K1+K5):
  * comb uint8[n, M, 8L] and hmat dtype[n, M]; hmat[:,0] = <x|H|x> over the first `nele`
- * occupied orbitals (cpu_tensor.cpp:260-261). */
-int pynqs_comb_hij_fused(const uint8_t *bra, const void *h1e, const void *h2e, int64_t n, int sorb, int nele,
-                         int noA, int noB, uint8_t *comb, void *hmat, int dtype, void *stream);
+ * occupied orbitals (cpu_tensor.cpp:260-261).  prep_ws: workspace filled by
+ * pynqs_prepare_integrals for the same (h2e, sorb, dtype), or NULL to read the packed arrays
+ * directly (slower, identical results). */
+int pynqs_comb_hij_fused(const uint8_t *bra, const void *h1e, const void *h2e, const void *prep_ws, int64_t n,
+                         int sorb, int nele, int noA, int noB, uint8_t *comb, void *hmat, int dtype, void *stream);
 
 /* replaces get_hij_torch (bind.cpp:39-64, cuda_tensor.cpp:97-141; kernels K3/K4):
  * ket3d != 0: ket uint8[n, m, 8L], out[i,j] = <bra_i|H|ket_ij>;
@@ -103,12 +111,14 @@ int pynqs_lut_hashed(const uint8_t *key, int64_t N, const uint8_t *onv, int64_t 
  * never materialising comb / Hmat:  for each sample x, psi0 = table value of x (0 if absent),
  *   eloc = sum over x' in {x} U SD(x) found in the table of (psi(x') / psi0) * <x|H|x'>.
  * psi: double[N] (psi_complex == 0) or interleaved complex128[N]; eloc / psi0 likewise [n].
- * scratch: pynqs_eloc_scratch_bytes(n, ...) bytes.  h1e/h2e are float64. */
+ * scratch: pynqs_eloc_scratch_bytes(n, ...) bytes.  h1e/h2e are float64; prep_ws = prepared
+ * float64 integrals of h2e (pynqs_prepare_integrals) or NULL (slower hit evaluation, same results).
+ * hash_ws must have been built by pynqs_hash_build for exactly this key table. */
 int pynqs_eloc_scratch_bytes(int64_t n, int sorb, int noA, int noB, int psi_complex, int64_t *bytes);
-int pynqs_eloc_sample_space(const uint8_t *bra, int64_t n, const double *h1e, const double *h2e, int sorb,
-                            int nele, int noA, int noB, const uint8_t *key, const void *psi, int psi_complex,
-                            int64_t N, const void *hash_ws, void *scratch, int64_t scratch_bytes, void *eloc,
-                            void *psi0, void *stream);
+int pynqs_eloc_sample_space(const uint8_t *bra, int64_t n, const double *h1e, const double *h2e,
+                            const void *prep_ws, int sorb, int nele, int noA, int noB, const uint8_t *key,
+                            const void *psi, int psi_complex, int64_t N, const void *hash_ws, void *scratch,
+                            int64_t scratch_bytes, void *eloc, void *psi0, void *stream);
 
 /* number of kernel launches issued by this library in this process (bench.py's gpu_launches). */
 int64_t pynqs_launch_count(void);

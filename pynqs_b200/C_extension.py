@@ -169,8 +169,50 @@ def get_comb_tensor(bra: Tensor, sorb: int, nele: int, noA: int, noB: int, flag_
     return comb, states
 
 
-def get_comb_hij_fused(bra: Tensor, h1e: Tensor, h2e: Tensor, sorb: int, nele: int, noA: int, noB: int) -> Tuple[Tensor, Tensor]:
-    """Fused enumeration + <x|H|x'> (C_extension.pyi:125-137): (comb uint8 [n, M, 8L], Hmat [n, M])."""
+class PreparedIntegrals:
+    """Gather-friendly device copy of the packed h2e (csrc/prepare.cu): same numbers, bit for bit."""
+
+    def __init__(self, h2e: Tensor, sorb: int):
+        dev = _need_cuda(h2e)
+        _contig(h2e, "h2e")
+        code = _fdtype(h2e, h2e)
+        nbytes = _lib.ctypes.c_int64()
+        _lib.check(_lib.load().pynqs_prepared_bytes(int(sorb), code, _lib.ctypes.byref(nbytes)))
+        self.sorb, self.dtype = sorb, h2e.dtype
+        self.workspace = torch.empty(max(nbytes.value, 16), dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(
+                _lib.load().pynqs_prepare_integrals(vp(h2e.data_ptr()), int(sorb), code, vp(self.workspace.data_ptr()), i64(nbytes.value), _stream(dev))
+            )
+
+    @property
+    def nbytes(self) -> int:
+        return self.workspace.numel()
+
+
+_prep_cache: dict = {}
+# preparing costs one pass over ~(sorb/2)^4 elements: only worth it when the call writes more than that
+_PREP_MIN_OUTPUT_RATIO = 4
+
+
+def _cached_prep(h2e: Tensor, sorb: int) -> PreparedIntegrals:
+    """Per-tensor-object cache: valid while the same h2e tensor object is alive and unmodified."""
+    k = id(h2e)
+    ent = _prep_cache.get(k)
+    if ent is not None:
+        ref, version, ptr, prep = ent
+        if ref() is h2e and version == h2e._version and ptr == h2e.data_ptr() and prep.sorb == sorb:
+            return prep
+    prep = PreparedIntegrals(h2e, sorb)
+    _prep_cache[k] = (weakref.ref(h2e, lambda _r, k=k: _prep_cache.pop(k, None)), h2e._version, h2e.data_ptr(), prep)
+    return prep
+
+
+def get_comb_hij_fused(bra: Tensor, h1e: Tensor, h2e: Tensor, sorb: int, nele: int, noA: int, noB: int,
+                       *, prepared: "PreparedIntegrals | None | bool" = None) -> Tuple[Tensor, Tensor]:
+    """Fused enumeration + <x|H|x'> (C_extension.pyi:125-137): (comb uint8 [n, M, 8L], Hmat [n, M]).
+    `prepared`: a PreparedIntegrals of h2e, None = build/cache one when the call is large enough,
+    False = read the packed arrays directly (identical results)."""
     dev = _need_cuda(bra, h1e, h2e)
     for t, nm in ((bra, "bra"), (h1e, "h1e"), (h2e, "h2e")):
         _contig(t, nm)
@@ -184,10 +226,17 @@ def get_comb_hij_fused(bra: Tensor, h1e: Tensor, h2e: Tensor, sorb: int, nele: i
     comb = torch.empty((n, M, 8 * L), dtype=torch.uint8, device=dev)
     hmat = torch.empty((n, M), dtype=h1e.dtype, device=dev)
     if n:
+        if prepared is None:
+            na = sorb // 2
+            big = n * M >= _PREP_MIN_OUTPUT_RATIO * (na**4 + sorb**3) or id(h2e) in _prep_cache
+            prepared = _cached_prep(h2e, sorb) if big else False
+        prep_ptr = prepared.workspace.data_ptr() if prepared else None
+        if prepared and (prepared.sorb != sorb or prepared.dtype != h2e.dtype):
+            raise ValueError("prepared integrals do not match sorb / dtype")
         with torch.cuda.device(dev):
             _lib.check(
                 _lib.load().pynqs_comb_hij_fused(
-                    vp(bra.data_ptr()), vp(h1e.data_ptr()), vp(h2e.data_ptr()), i64(n), int(sorb), int(nele),
+                    vp(bra.data_ptr()), vp(h1e.data_ptr()), vp(h2e.data_ptr()), vp(prep_ptr), i64(n), int(sorb), int(nele),
                     int(noA), int(noB), vp(comb.data_ptr()), vp(hmat.data_ptr()), code, _stream(dev),
                 )
             )
@@ -302,6 +351,7 @@ def wavefunction_lut(bra_key: Tensor, onv: Tensor, sorb: int, little_endian: boo
 def eloc_sample_space(
     bra: Tensor, h1e: Tensor, h2e: Tensor, sorb: int, nele: int, noA: int, noB: int,
     bra_key: Tensor, wf_value: Tensor, hash_index: HashIndex | None = None,
+    prepared: "PreparedIntegrals | None | bool" = None,
 ) -> Tuple[Tensor, Tensor]:
     """Additive op: the whole sample-space local energy of vmc/energy/eloc.py:326-397 in one pass.
     Returns (eloc [n], psi0 [n]) in wf_value's dtype (float64 or complex128).  bra_key must be the
@@ -325,6 +375,11 @@ def eloc_sample_space(
         return eloc, psi0
     if hash_index is None:
         hash_index = _cached_hash(bra_key)
+    if prepared is None:
+        prepared = _cached_prep(h2e, sorb)
+    prep_ptr = prepared.workspace.data_ptr() if prepared else None
+    if prepared and (prepared.sorb != sorb or prepared.dtype != torch.float64):
+        raise ValueError("prepared integrals do not match sorb / dtype")
     lib = _lib.load()
     nbytes = _lib.ctypes.c_int64()
     _lib.check(lib.pynqs_eloc_scratch_bytes(i64(n), int(sorb), int(noA), int(noB), cplx, _lib.ctypes.byref(nbytes)))
@@ -332,7 +387,7 @@ def eloc_sample_space(
     with torch.cuda.device(dev):
         _lib.check(
             lib.pynqs_eloc_sample_space(
-                vp(bra.data_ptr()), i64(n), vp(h1e.data_ptr()), vp(h2e.data_ptr()), int(sorb), int(nele), int(noA), int(noB),
+                vp(bra.data_ptr()), i64(n), vp(h1e.data_ptr()), vp(h2e.data_ptr()), vp(prep_ptr), int(sorb), int(nele), int(noA), int(noB),
                 vp(bra_key.data_ptr()), vp(wf_value.data_ptr()), cplx, i64(N), vp(hash_index.workspace.data_ptr()),
                 vp(scratch.data_ptr()), i64(nbytes.value), vp(eloc.data_ptr()), vp(psi0.data_ptr()), _stream(dev),
             )

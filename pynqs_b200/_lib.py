@@ -11,7 +11,8 @@ LIB_PATH = os.path.join(HERE, "csrc", "libpynqs_b200.so")
 # every symbol include/pynqs_b200.h declares (tests check the header against this list)
 SYMBOLS = [
     "pynqs_abi_version", "pynqs_last_error", "pynqs_check_sorb", "pynqs_num_sd",
-    "pynqs_tensor_to_onv", "pynqs_onv_to_tensor", "pynqs_comb", "pynqs_comb_hij_fused", "pynqs_hij",
+    "pynqs_tensor_to_onv", "pynqs_onv_to_tensor", "pynqs_comb", "pynqs_prepared_bytes", "pynqs_prepare_integrals",
+    "pynqs_comb_hij_fused", "pynqs_hij",
     "pynqs_lut", "pynqs_hash_bytes", "pynqs_hash_build", "pynqs_lut_hashed",
     "pynqs_eloc_scratch_bytes", "pynqs_eloc_sample_space", "pynqs_launch_count",
 ]

@@ -33,8 +33,12 @@ void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 // launchers implemented in the other translation units
 int launch_comb(const u64 *, u64 *, long long, const ExcGeom &, cudaStream_t);
-int launch_comb_hij_f64(const u64 *, const double *, const double *, u64 *, double *, long long, const ExcGeom &, cudaStream_t);
-int launch_comb_hij_f32(const u64 *, const float *, const float *, u64 *, float *, long long, const ExcGeom &, cudaStream_t);
+int launch_comb_hij_f64(const u64 *, const double *, const double *, const void *, u64 *, double *, long long, const ExcGeom &,
+                        cudaStream_t);
+int launch_comb_hij_f32(const u64 *, const float *, const float *, const void *, u64 *, float *, long long, const ExcGeom &,
+                        cudaStream_t);
+long long prepared_bytes(int, int);
+int launch_prepare(const void *, int, int, void *, long long, cudaStream_t);
 int launch_states(const u64 *, double *, long long, int, cudaStream_t);
 template <typename T>
 int launch_hij(const u64 *, const u64 *, const T *, const T *, T *, long long, long long, int, int, int, cudaStream_t);
@@ -43,7 +47,7 @@ long long hash_workspace_bytes(long long);
 int launch_hash_build(const u64 *, long long, int, void *, long long, cudaStream_t);
 int launch_lut_hashed(const u64 *, long long, const u64 *, long long, int, const void *, long long *, unsigned char *, cudaStream_t);
 long long eloc_scratch_bytes(long long, int, int);
-int launch_eloc(const u64 *, long long, const double *, const double *, const u64 *, const double *, int, long long,
+int launch_eloc(const u64 *, long long, const double *, const double *, const void *, const u64 *, const double *, int, long long,
                 const void *, void *, long long, double *, double *, const ExcGeom &, cudaStream_t);
 int launch_onv_to_tensor(const u64 *, void *, int, long long, int, cudaStream_t);
 int launch_tensor_to_onv(const unsigned char *, unsigned char *, long long, int, cudaStream_t);
@@ -140,8 +144,27 @@ int pynqs_comb(const uint8_t *bra, int64_t n, int sorb, int noA, int noB, uint8_
   return 0;
 }
 
-int pynqs_comb_hij_fused(const uint8_t *bra, const void *h1e, const void *h2e, int64_t n, int sorb, int nele, int noA,
-                         int noB, uint8_t *comb, void *hmat, int dtype, void *stream) {
+int pynqs_prepared_bytes(int sorb, int dtype, int64_t *bytes) {
+  if (int rc = check_geometry(sorb, 0, 0, 0)) return rc;
+  if (dtype != PYNQS_F32 && dtype != PYNQS_F64) {
+    set_error("prepared_bytes: dtype %d is neither float32 nor float64", dtype);
+    return PYNQS_EVALUE;
+  }
+  *bytes = prepared_bytes(sorb, dtype);
+  return 0;
+}
+
+int pynqs_prepare_integrals(const void *h2e, int sorb, int dtype, void *prep_ws, int64_t prep_bytes, void *stream) {
+  if (int rc = check_geometry(sorb, 0, 0, 0)) return rc;
+  if (dtype != PYNQS_F32 && dtype != PYNQS_F64) {
+    set_error("prepare_integrals: dtype %d is neither float32 nor float64", dtype);
+    return PYNQS_EVALUE;
+  }
+  return launch_prepare(h2e, sorb, dtype, prep_ws, prep_bytes, (cudaStream_t)stream);
+}
+
+int pynqs_comb_hij_fused(const uint8_t *bra, const void *h1e, const void *h2e, const void *prep_ws, int64_t n, int sorb,
+                         int nele, int noA, int noB, uint8_t *comb, void *hmat, int dtype, void *stream) {
   if (int rc = check_geometry(sorb, nele, noA, noB)) return rc;
   long long nsd;
   if (int rc = num_sd_checked(sorb, noA, noB, &nsd)) return rc;
@@ -153,9 +176,9 @@ int pynqs_comb_hij_fused(const uint8_t *bra, const void *h1e, const void *h2e, i
   const ExcGeom g = make_geom(sorb, nele, noA, noB);
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == PYNQS_F64)
-    return launch_comb_hij_f64(reinterpret_cast<const u64 *>(bra), (const double *)h1e, (const double *)h2e,
+    return launch_comb_hij_f64(reinterpret_cast<const u64 *>(bra), (const double *)h1e, (const double *)h2e, prep_ws,
                                reinterpret_cast<u64 *>(comb), (double *)hmat, n, g, st);
-  return launch_comb_hij_f32(reinterpret_cast<const u64 *>(bra), (const float *)h1e, (const float *)h2e,
+  return launch_comb_hij_f32(reinterpret_cast<const u64 *>(bra), (const float *)h1e, (const float *)h2e, prep_ws,
                              reinterpret_cast<u64 *>(comb), (float *)hmat, n, g, st);
 }
 
@@ -220,15 +243,15 @@ int pynqs_eloc_scratch_bytes(int64_t n, int sorb, int noA, int noB, int psi_comp
   return 0;
 }
 
-int pynqs_eloc_sample_space(const uint8_t *bra, int64_t n, const double *h1e, const double *h2e, int sorb, int nele,
-                            int noA, int noB, const uint8_t *key, const void *psi, int psi_complex, int64_t N,
+int pynqs_eloc_sample_space(const uint8_t *bra, int64_t n, const double *h1e, const double *h2e, const void *prep_ws,
+                            int sorb, int nele, int noA, int noB, const uint8_t *key, const void *psi, int psi_complex, int64_t N,
                             const void *hash_ws, void *scratch, int64_t scratch_bytes, void *eloc, void *psi0,
                             void *stream) {
   if (int rc = check_geometry(sorb, nele, noA, noB)) return rc;
   long long nsd;
   if (int rc = num_sd_checked(sorb, noA, noB, &nsd)) return rc;
   const ExcGeom g = make_geom(sorb, nele, noA, noB);
-  return launch_eloc(reinterpret_cast<const u64 *>(bra), n, h1e, h2e, reinterpret_cast<const u64 *>(key),
+  return launch_eloc(reinterpret_cast<const u64 *>(bra), n, h1e, h2e, prep_ws, reinterpret_cast<const u64 *>(key),
                      (const double *)psi, psi_complex, N, hash_ws, scratch, scratch_bytes, (double *)eloc, (double *)psi0, g,
                      (cudaStream_t)stream);
 }

@@ -146,6 +146,11 @@ constexpr u64 kOdd = 0xAAAAAAAAAAAAAAAAull;   // beta spin orbitals
 struct OrbLists {
   unsigned short a[kMaxHalf];
   unsigned short b[kMaxHalf];
+  // occupied orbitals in the order the reference sums a single excitation's two-electron terms:
+  // words ascending, bits DEscending inside a word (cpp_src/cpu/hamiltonian.cpp:59-68)
+  unsigned char occ_order[2 * kMaxHalf];
+  int n_occ;
+  int pad[3];
 };
 
 // One warp builds both lists: lane handles orbitals lane, lane+32, ...  The bra word itself is
@@ -168,6 +173,22 @@ __device__ __forceinline__ void build_lists(const Onv<L> &x, int sorb, int noA, 
     const unsigned short e = (unsigned short)(k | ((occ_all & 1) << 8));
     if (k & 1) out.b[slot] = e;
     else out.a[slot] = e;
+    if (occ) {
+      // position in the single-excitation summation order
+      int pos = 0;
+#pragma unroll
+      for (int j = 0; j < L; ++j) {
+        if (j < (k >> 6)) pos += __popcll(x.w[j]);
+        else if (j == (k >> 6)) pos += __popcll(x.w[j] >> (k & 63)) - 1;  // occupied bits above k in its word
+      }
+      out.occ_order[pos] = (unsigned char)k;
+    }
+  }
+  if (lane == 0) {
+    int c = 0;
+#pragma unroll
+    for (int j = 0; j < L; ++j) c += __popcll(x.w[j]);
+    out.n_occ = c;
   }
 }
 

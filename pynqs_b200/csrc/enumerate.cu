@@ -4,19 +4,24 @@
 // (get_comb_SD_kernel, :195-222) and K5 (get_comb_SD_fused_kernel, :224-277) plus the
 // `repeat` pre-fill of cuda_tensor.cpp:239.  Differences in design, not in results:
 //   * no merged[n, sorb] tensor in HBM: one warp derives the occupied/virtual lists from
-//     popcounts of the bra words and keeps them in shared memory;
-//   * every output byte is written exactly once, as 16-byte vectors: a thread owns two
-//     consecutive rows (flat row index even), so comb stores are ulonglong2 and Hmat stores
-//     are double2;
+//     popcounts of the bra words; all threads then build the per-sample excitation tables
+//     (tables.cuh) in shared memory, so a row costs one exact multiply-shift division, two LDS
+//     and one coalesced-ish gather from the prepared integrals (prepare.cu);
+//   * every output byte is written exactly once: the 32 lanes of a warp own 32 consecutive rows,
+//     so one store instruction writes 256 (L = 1) or 512 (L = 2, ulonglong2 per lane) contiguous
+//     bytes of comb and 256 contiguous bytes of Hmat;
 //   * 64-bit flat indexing (the reference overflows int beyond 2^31 elements);
 //   * the diagonal <x|H|x> runs in its own thread-per-sample kernel, so no lane of the
 //     enumeration warps serialises nele^2/2 gathers.
-#include "common.cuh"
+// Two kernels: enumerate_kernel (tables + prepared integrals; the production path) and
+// enumerate_plain_kernel (decodes every row from the packed arrays; used when no prepared
+// workspace is given, and as an on-device cross-check in the tests).
+#include "prepare.cuh"
+#include "tables.cuh"
 
 namespace pynqs {
 
 constexpr int kEnumThreads = 256;
-constexpr int kEnumTileRows = 4096;  // rows of one sample handled by one CTA
 
 template <int L>
 __device__ __forceinline__ void store_pair_rows(u64 *dst, const Onv<L> &r0, const Onv<L> &r1) {
@@ -38,10 +43,214 @@ __device__ __forceinline__ void store_row(u64 *dst, const Onv<L> &r) {
   for (int i = 0; i < L; ++i) dst[i] = r.w[i];
 }
 
+template <typename T>
+__device__ __forceinline__ void store_pair_vals(T *dst, T a, T b);
+template <>
+__device__ __forceinline__ void store_pair_vals<double>(double *dst, double a, double b) {
+  *reinterpret_cast<double2 *>(dst) = make_double2(a, b);
+}
+template <>
+__device__ __forceinline__ void store_pair_vals<float>(float *dst, float a, float b) {
+  *reinterpret_cast<float2 *>(dst) = make_float2(a, b);
+}
+
+// ---- table entries of the enumeration kernel: excitation mask (L = 1) + HitInfo (tables.cuh) ------
+template <int L>
+struct __align__(8) EnumEntry {
+  u32 off, cmp;
+};
+template <>
+struct __align__(16) EnumEntry<1> {
+  u64 mask;
+  u32 off, cmp;
+};
+
+template <int L>
+__device__ __forceinline__ EnumEntry<L> load_entry(const EnumEntry<L> *p) {
+  const uint2 v = *reinterpret_cast<const uint2 *>(p);
+  EnumEntry<L> e;
+  e.off = v.x;
+  e.cmp = v.y;
+  return e;
+}
+template <>
+__device__ __forceinline__ EnumEntry<1> load_entry<1>(const EnumEntry<1> *p) {
+  // one LDS.128 (the compiler splits a plain 16-byte shared load into two LDS.64, which doubles
+  // the shared-memory wavefronts of the stride-16 access pattern)
+  uint4 v;
+  const unsigned a = (unsigned)__cvta_generic_to_shared(p);
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  EnumEntry<1> e;
+  e.mask = (u64)v.x | ((u64)v.y << 32);
+  e.off = v.z;
+  e.cmp = v.w;
+  return e;
+}
+
+template <int L>
+__device__ __forceinline__ void set_mask(EnumEntry<L> &, u32, u32) {}
+template <>
+__device__ __forceinline__ void set_mask<1>(EnumEntry<1> &e, u32 a, u32 b) {
+  e.mask = (1ull << a) | (1ull << b);
+}
+
+template <int L>
+__device__ __forceinline__ Onv<L> entry_apply(const Onv<L> &x, const EnumEntry<L> &e) {
+  Onv<L> y = x;
+  flip_bit<L>(y, (int)(e.cmp & 0xffu));
+  flip_bit<L>(y, (int)((e.cmp >> 16) & 0xffu));
+  return y;
+}
+template <>
+__device__ __forceinline__ Onv<1> entry_apply<1>(const Onv<1> &x, const EnumEntry<1> &e) {
+  Onv<1> y;
+  y.w[0] = x.w[0] ^ e.mask;
+  return y;
+}
+
+template <int L>
+__device__ __forceinline__ void store_row_vec(u64 *dst, const Onv<L> &r) {
+  if (L == 2) {
+    *reinterpret_cast<ulonglong2 *>(dst) = make_ulonglong2(r.w[0], r.w[L - 1]);  // 16-byte rows: one vector store
+  } else {
+#pragma unroll
+    for (int i = 0; i < L; ++i) dst[i] = r.w[i];
+  }
+}
+
+constexpr int kRowsPerThread = 4;  // independent rows (and integral gathers) in flight per thread
+
+// Rows [lo, hi) of one excitation class (CLS: 0/1 single a/b, 2/3 double aa/bb, 4 double ab);
+// row m holds excitation r = m - 1.  A warp takes chunks of 32 * ROWS consecutive rows; lane l
+// owns rows chunk + l + 32 j, so each store instruction of the warp covers 32 consecutive rows
+// (256 contiguous bytes of comb at L = 1 and of Hmat): coalesced, every byte written once.
+template <int L, typename T, bool WITH_H, int CLS, int ROWS>
+__device__ __forceinline__ void enumerate_class(const Onv<L> &x, const EnumEntry<L> *__restrict__ tab, const TableOffsets &to,
+                                                const ExcGeom &g, const OrbLists &lists, const T *__restrict__ h1e,
+                                                const PrepView<T> &prep, u64 *__restrict__ comb_s, T *__restrict__ hmat_s,
+                                                int lo, int hi) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int kChunk = 32 * ROWS;
+  for (int c = lo + warp * kChunk; c < hi; c += (kEnumThreads / 32) * kChunk) {
+    Onv<L> row[ROWS];
+    T val[ROWS];
+    u32 sgn[ROWS];
+#pragma unroll
+    for (int j = 0; j < ROWS; ++j) {
+      const int m = c + lane + 32 * j;
+      row[j] = x;
+      val[j] = (T)0.0;
+      sgn[j] = 0;
+      if (m < hi) {
+        const u32 r = (u32)(m - 1);
+        if (CLS <= 1) {
+          const EnumEntry<L> e1 = load_entry<L>(tab + (CLS == 0 ? to.sa + (int)r : to.sb + (int)(r - g.d0)));
+          row[j] = entry_apply<L>(x, e1);
+          if (WITH_H) {
+            // single h -> p: h1e(h,p) + sum over occupied k, in the reference's order, of <hk||pk>
+            // SA packs hA | pA << 16, SB packs pB | hB << 16
+            const u32 h = CLS == 0 ? (e1.cmp & 0xffu) : (e1.cmp >> 16), p = CLS == 0 ? (e1.cmp >> 16) : (e1.cmp & 0xffu);
+            const u32 na = (u32)prep.na;
+            const size_t kstride = (size_t)2 * na * na;
+            const int n_occ = lists.n_occ;
+            T v = (T)0.0;
+            v += __ldg(h1e + (size_t)p * g.sorb + h);
+            const T *line = prep.s + ((size_t)(h & 1u) * na + (p >> 1)) * na + (h >> 1);
+            for (int q = 0; q < n_occ; q += 4) {
+              T t[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) t[i] = (q + i < n_occ) ? __ldg(line + kstride * lists.occ_order[q + i]) : (T)0.0;
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                if (q + i < n_occ) v += t[i];
+            }
+            val[j] = v;
+            sgn[j] = e1.off;  // bit 31 = the single's sign
+          }
+        } else {
+          int t1, t2;
+          if (CLS == 4) {
+            const u32 q = r - (u32)g.d3;
+            const u32 jb = fdiv(q, g.by_sA);
+            t1 = to.sa + (int)(q - jb * g.sA);
+            t2 = to.sb + (int)jb;
+          } else if (CLS == 2) {
+            t1 = to.hpa + (int)(r - fdiv(r, g.by_noAA) * g.noAA);  // r % noAA with the GLOBAL r (quirk Q1)
+            t2 = to.ppa + (int)fdiv(r - (u32)g.d1, g.by_noAA);
+          } else {
+            t1 = to.hpb + (int)(r - fdiv(r, g.by_noBB) * g.noBB);
+            t2 = to.ppb + (int)fdiv(r - (u32)g.d2, g.by_noBB);
+          }
+          const EnumEntry<L> e1 = load_entry<L>(tab + t1);
+          const EnumEntry<L> e2 = load_entry<L>(tab + t2);
+          row[j] = entry_apply<L>(entry_apply<L>(x, e1), e2);
+          if (WITH_H) {
+            const HitInfo i1 = {e1.off, e1.cmp}, i2 = {e2.off, e2.cmp};
+            const T *tbl = CLS == 4 ? prep.ab : (CLS == 2 ? prep.aa : prep.bb);
+            val[j] = __ldg(tbl + ((i1.off + i2.off) & 0x7fffffffu));
+            sgn[j] = double_sign_word(CLS == 4, i1, i2);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < ROWS; ++j) {
+      const int m = c + lane + 32 * j;
+      if (m < hi) {
+        store_row_vec<L>(comb_s + (size_t)m * L, row[j]);
+        if (WITH_H) hmat_s[m] = flip_sign((T)1.0 * val[j], sgn[j]);
+      }
+    }
+  }
+}
+
+// One CTA = one tile of one sample.
 template <int L, typename T, bool WITH_H>
 __global__ void __launch_bounds__(kEnumThreads)
-enumerate_kernel(const u64 *__restrict__ bra, const T *__restrict__ h1e, const T *__restrict__ h2e, u64 *__restrict__ comb,
-                 T *__restrict__ hmat, long long n, int tiles_per_sample, ExcGeom g) {
+enumerate_kernel(const u64 *__restrict__ bra, const T *__restrict__ h1e, PrepView<T> prep, u64 *__restrict__ comb,
+                 T *__restrict__ hmat, long long n, int tiles_per_sample, int tile_rows, ExcGeom g) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  OrbLists &lists = *reinterpret_cast<OrbLists *>(smem_raw);
+  EnumEntry<L> *tab = reinterpret_cast<EnumEntry<L> *>(smem_raw + sizeof(OrbLists));
+
+  const long long s = blockIdx.x / tiles_per_sample;
+  const int tile = blockIdx.x - (int)(s * tiles_per_sample);
+  if (s >= n) return;
+  const Onv<L> x = load_onv<L>(bra + s * L);
+  if (threadIdx.x < 32) build_lists<L>(x, g.sorb, g.noA, g.noB, lists, threadIdx.x);
+  __syncthreads();
+  const TableOffsets to = table_offsets(g);
+  const u32 na = (u32)prep.na, npair = (u32)prep.npair;
+  for_each_table_entry(g, lists, to, [&](int t, int kind, u32 e0, u32 e1) {
+    EnumEntry<L> e;
+    const HitInfo hi = make_hit_info(kind, e0, e1, na, npair);
+    e.off = hi.off;
+    e.cmp = hi.cmp;
+    set_mask<L>(e, e0 & 0xffu, e1 & 0xffu);
+    tab[t] = e;
+  });
+  __syncthreads();
+
+  const long long M = (long long)g.nsd + 1;
+  u64 *comb_s = comb + s * M * L;   // this sample's rows
+  T *hmat_s = WITH_H ? hmat + s * M : nullptr;
+  const long long tb = (long long)tile * tile_rows;
+  const int t_lo = (int)tb, t_hi = (int)(tb + tile_rows < M ? tb + tile_rows : M);
+  if (tile == 0 && threadIdx.x == 0) store_row_vec<L>(comb_s, x);  // row 0 = bra (its H belongs to diag_kernel)
+  auto clip_lo = [&](int v) { return v > t_lo ? v : t_lo; };
+  auto clip_hi = [&](int v) { return v < t_hi ? v : t_hi; };
+  enumerate_class<L, T, WITH_H, 0, 1>(x, tab, to, g, lists, h1e, prep, comb_s, hmat_s, clip_lo(1), clip_hi(g.d0 + 1));
+  enumerate_class<L, T, WITH_H, 1, 1>(x, tab, to, g, lists, h1e, prep, comb_s, hmat_s, clip_lo(g.d0 + 1), clip_hi(g.d1 + 1));
+  enumerate_class<L, T, WITH_H, 2, kRowsPerThread>(x, tab, to, g, lists, h1e, prep, comb_s, hmat_s, clip_lo(g.d1 + 1), clip_hi(g.d2 + 1));
+  enumerate_class<L, T, WITH_H, 3, kRowsPerThread>(x, tab, to, g, lists, h1e, prep, comb_s, hmat_s, clip_lo(g.d2 + 1), clip_hi(g.d3 + 1));
+  enumerate_class<L, T, WITH_H, 4, kRowsPerThread>(x, tab, to, g, lists, h1e, prep, comb_s, hmat_s, clip_lo(g.d3 + 1), clip_hi((int)M));
+}
+
+// ---- plain variant: every row decoded from the packed arrays ----------------------------------------
+template <int L, typename T, bool WITH_H>
+__global__ void __launch_bounds__(kEnumThreads)
+enumerate_plain_kernel(const u64 *__restrict__ bra, const T *__restrict__ h1e, const T *__restrict__ h2e, u64 *__restrict__ comb,
+                       T *__restrict__ hmat, long long n, int tiles_per_sample, int tile_rows, ExcGeom g) {
   __shared__ OrbLists lists;
   const long long s = blockIdx.x / tiles_per_sample;
   const int tile = blockIdx.x - (int)(s * tiles_per_sample);
@@ -51,11 +260,11 @@ enumerate_kernel(const u64 *__restrict__ bra, const T *__restrict__ h1e, const T
   __syncthreads();
 
   const long long M = (long long)g.nsd + 1;
-  const long long base = s * M;           // flat index of row 0 of this sample
-  const int odd = (int)(base & 1);        // rows are paired so that base + m is even
-  const long long m_lo = (long long)tile * kEnumTileRows - odd;
-  for (int u = threadIdx.x; u < kEnumTileRows / 2; u += kEnumThreads) {
-    const long long m0 = m_lo + 2 * u;  // base + m0 is even
+  const long long base = s * M;
+  const int odd = (int)(base & 1);
+  const long long m_lo = (long long)tile * tile_rows - odd;
+  for (int u = threadIdx.x; u < tile_rows / 2; u += kEnumThreads) {
+    const long long m0 = m_lo + 2 * u;
     if (m0 >= M) break;
     Onv<L> row[2];
     T val[2];
@@ -75,13 +284,8 @@ enumerate_kernel(const u64 *__restrict__ bra, const T *__restrict__ h1e, const T
     if (ok[0] && ok[1]) {
       store_pair_rows<L>(comb + (base + m0) * L, row[0], row[1]);
       if (WITH_H) {
-        if (m0 == 0) {
-          hmat[base + 1] = val[1];  // row 0 belongs to the diagonal kernel
-        } else if (sizeof(T) == 8) {
-          *reinterpret_cast<double2 *>(hmat + base + m0) = make_double2((double)val[0], (double)val[1]);
-        } else {
-          *reinterpret_cast<float2 *>(hmat + base + m0) = make_float2((float)val[0], (float)val[1]);
-        }
+        if (m0 == 0) hmat[base + 1] = val[1];
+        else store_pair_vals<T>(hmat + base + m0, val[0], val[1]);
       }
     } else {
 #pragma unroll
@@ -94,7 +298,7 @@ enumerate_kernel(const u64 *__restrict__ bra, const T *__restrict__ h1e, const T
   }
 }
 
-// thread-per-sample diagonal: hmat[s*M] = <x|H|x>
+// thread-per-sample diagonal: out[s * stride] = <x|H|x>
 template <int L, typename T>
 __global__ void __launch_bounds__(128)
 diag_kernel(const u64 *__restrict__ bra, const T *__restrict__ h1e, const T *__restrict__ h2e, T *__restrict__ out,
@@ -119,19 +323,47 @@ states_kernel(const u64 *__restrict__ comb, double *__restrict__ states, long lo
   }
 }
 
+// rows of one sample per CTA: whole sample when that still gives >= ~8 CTAs per SM, else split
+static void choose_tiling(long long n, long long M, int &tiles, int &tile_rows) {
+  const long long rows = M;
+  long long want_tiles = 1;
+  if (n > 0 && n < 148LL * 8) want_tiles = (148LL * 8 + n - 1) / n;
+  long long tr = (rows + want_tiles - 1) / want_tiles;
+  if (tr < 2048) tr = 2048;
+  if (tr > 32768) tr = 32768;
+  tr = (tr + 511) / 512 * 512;
+  tile_rows = (int)tr;
+  tiles = (int)((rows + tr - 1) / tr);
+}
+
 template <int L, typename T, bool WITH_H>
-static int launch_enumerate_L(const u64 *bra, const T *h1e, const T *h2e, u64 *comb, T *hmat, long long n, const ExcGeom &g,
-                              cudaStream_t st) {
+static int launch_enumerate_L(const u64 *bra, const T *h1e, const T *h2e, const void *prep_ws, u64 *comb, T *hmat, long long n,
+                              const ExcGeom &g, cudaStream_t st) {
   const long long M = (long long)g.nsd + 1;
-  const int tiles = (int)((M + 1 + kEnumTileRows - 1) / kEnumTileRows);
+  int tiles, tile_rows;
+  choose_tiling(n, M, tiles, tile_rows);
   const long long blocks = n * tiles;
   if (blocks > 0x7fffffffLL) {
     set_error("enumerate: n * tiles = %lld exceeds the grid limit; split the batch", blocks);
     return 1;
   }
-  enumerate_kernel<L, T, WITH_H><<<(unsigned)blocks, kEnumThreads, 0, st>>>(bra, h1e, h2e, comb, hmat, n, tiles, g);
-  count_launch();
-  if (int rc = check_launch("enumerate_kernel")) return rc;
+  const bool use_tables = (prep_ws != nullptr) || !WITH_H;
+  if (use_tables) {
+    const size_t smem = sizeof(OrbLists) + sizeof(EnumEntry<L>) * (size_t)table_offsets(g).total;
+    auto kern = enumerate_kernel<L, T, WITH_H>;
+    if (smem > 48 * 1024) {
+      if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        return check_launch("enumerate_kernel smem opt-in");
+    }
+    PrepView<T> pv = prep_view<T>(prep_ws, g.sorb);
+    kern<<<(unsigned)blocks, kEnumThreads, smem, st>>>(bra, h1e, pv, comb, hmat, n, tiles, tile_rows, g);
+    count_launch();
+    if (int rc = check_launch("enumerate_kernel")) return rc;
+  } else {
+    enumerate_plain_kernel<L, T, WITH_H><<<(unsigned)blocks, kEnumThreads, 0, st>>>(bra, h1e, h2e, comb, hmat, n, tiles, tile_rows, g);
+    count_launch();
+    if (int rc = check_launch("enumerate_plain_kernel")) return rc;
+  }
   if (WITH_H) {
     diag_kernel<L, T><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(bra, h1e, h2e, hmat, n, M, g.sorb, g.nele);
     count_launch();
@@ -141,29 +373,29 @@ static int launch_enumerate_L(const u64 *bra, const T *h1e, const T *h2e, u64 *c
 }
 
 template <typename T, bool WITH_H>
-static int launch_enumerate_T(const u64 *bra, const T *h1e, const T *h2e, u64 *comb, T *hmat, long long n, const ExcGeom &g,
-                              cudaStream_t st) {
+static int launch_enumerate_T(const u64 *bra, const T *h1e, const T *h2e, const void *prep_ws, u64 *comb, T *hmat, long long n,
+                              const ExcGeom &g, cudaStream_t st) {
   switch (g.L) {
-    case 1: return launch_enumerate_L<1, T, WITH_H>(bra, h1e, h2e, comb, hmat, n, g, st);
-    case 2: return launch_enumerate_L<2, T, WITH_H>(bra, h1e, h2e, comb, hmat, n, g, st);
-    case 3: return launch_enumerate_L<3, T, WITH_H>(bra, h1e, h2e, comb, hmat, n, g, st);
+    case 1: return launch_enumerate_L<1, T, WITH_H>(bra, h1e, h2e, prep_ws, comb, hmat, n, g, st);
+    case 2: return launch_enumerate_L<2, T, WITH_H>(bra, h1e, h2e, prep_ws, comb, hmat, n, g, st);
+    case 3: return launch_enumerate_L<3, T, WITH_H>(bra, h1e, h2e, prep_ws, comb, hmat, n, g, st);
   }
   set_error("unsupported ONV length L=%d", g.L);
   return 1;
 }
 
 int launch_comb(const u64 *bra, u64 *comb, long long n, const ExcGeom &g, cudaStream_t st) {
-  return launch_enumerate_T<double, false>(bra, nullptr, nullptr, comb, nullptr, n, g, st);
+  return launch_enumerate_T<double, false>(bra, nullptr, nullptr, nullptr, comb, nullptr, n, g, st);
 }
 
-int launch_comb_hij_f64(const u64 *bra, const double *h1e, const double *h2e, u64 *comb, double *hmat, long long n,
-                        const ExcGeom &g, cudaStream_t st) {
-  return launch_enumerate_T<double, true>(bra, h1e, h2e, comb, hmat, n, g, st);
+int launch_comb_hij_f64(const u64 *bra, const double *h1e, const double *h2e, const void *prep_ws, u64 *comb, double *hmat,
+                        long long n, const ExcGeom &g, cudaStream_t st) {
+  return launch_enumerate_T<double, true>(bra, h1e, h2e, prep_ws, comb, hmat, n, g, st);
 }
 
-int launch_comb_hij_f32(const u64 *bra, const float *h1e, const float *h2e, u64 *comb, float *hmat, long long n,
-                        const ExcGeom &g, cudaStream_t st) {
-  return launch_enumerate_T<float, true>(bra, h1e, h2e, comb, hmat, n, g, st);
+int launch_comb_hij_f32(const u64 *bra, const float *h1e, const float *h2e, const void *prep_ws, u64 *comb, float *hmat,
+                        long long n, const ExcGeom &g, cudaStream_t st) {
+  return launch_enumerate_T<float, true>(bra, h1e, h2e, prep_ws, comb, hmat, n, g, st);
 }
 
 // stand-alone diagonal (used by the fused local-energy op): out[s * stride] = <x_s|H|x_s>
@@ -184,8 +416,8 @@ int launch_diag_f64(const u64 *bra, const double *h1e, const double *h2e, double
 int launch_states(const u64 *comb, double *states, long long rows, int sorb, cudaStream_t st) {
   const int L = (sorb - 1) / 64 + 1;
   const long long total = rows * sorb;
-  const unsigned blocks = (unsigned)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
   if (total == 0) return 0;
+  const unsigned blocks = (unsigned)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
   switch (L) {
     case 1: states_kernel<1><<<blocks, 256, 0, st>>>(comb, states, rows, sorb); break;
     case 2: states_kernel<2><<<blocks, 256, 0, st>>>(comb, states, rows, sorb); break;

@@ -1,5 +1,13 @@
 // lut.cu -- wavefunction_lut kernels: classic binary search (K6 replacement, cuda/kernel.cu:608-680)
-// and the hash index (build + probe) used to accelerate large query batches.
+// and the string-grouped index (build + probe) of lut.cuh.
+//
+// Build, all asynchronous on the caller's stream (no host round trip, no sort):
+//   1. count : every key claims / finds the directory slot of its beta string and of its alpha
+//              string (64-bit CAS) and bumps the slot's key count;
+//   2. carve : every used slot takes a power-of-two run of buckets (<= 1 key per 4-slot bucket on
+//              average) from the shared pool with one atomicAdd;
+//   3. fill  : every key inserts (tag, row) into its two regions (32-bit CAS, linear probing
+//              inside the region).
 #include "lut.cuh"
 
 namespace pynqs {
@@ -18,25 +26,38 @@ lut_classic_kernel(const u64 *__restrict__ key, long long N, const u64 *__restri
 
 template <int L>
 __global__ void __launch_bounds__(256)
-lut_hashed_kernel(const u64 *__restrict__ key, long long N, const HashHeader *__restrict__ hdr, const u64 *__restrict__ q,
-                  long long n, long long *__restrict__ idx, unsigned char *__restrict__ mask) {
+lut_indexed_kernel(const u64 *__restrict__ key, long long N, IndexView iv, const u64 *__restrict__ q, long long n,
+                   long long *__restrict__ idx, unsigned char *__restrict__ mask) {
+  const bool dup = iv.hdr->has_dup != 0;  // duplicates: reproduce the reference's probe sequence instead
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
     const Onv<L> x = load_onv<L>(q + t * L);
-    const long long r = hashed_search<L>(key, N, hdr, x);
+    const long long r = dup ? classic_search<L>(key, N, x) : indexed_search<L>(key, iv, x);
     idx[t] = r;
     mask[t] = r >= 0;
   }
 }
 
-__global__ void hash_header_kernel(HashHeader *hdr, u32 log2_nb, u64 N) {
-  hdr->log2_nb = log2_nb;
+__global__ void index_header_kernel(HashHeader *hdr, u32 log2_dir, u64 N, u32 pool_buckets) {
+  hdr->log2_dir = log2_dir;
   hdr->has_dup = 0;
   hdr->n_keys = N;
+  hdr->cursor = 0;
+  hdr->pool_buckets = pool_buckets;
+}
+
+__device__ __forceinline__ u32 dir_claim(DirSlot *dir, u32 log2_dir, u64 h) {
+  const u32 mask = (1u << log2_dir) - 1u;
+  u32 s = (u32)(h >> (64 - log2_dir));
+  for (;;) {
+    const u64 prev = atomicCAS(reinterpret_cast<unsigned long long *>(&dir[s].h), (unsigned long long)kDirEmpty, (unsigned long long)h);
+    if (prev == kDirEmpty || prev == h) return s;
+    s = (s + 1) & mask;
+  }
 }
 
 template <int L>
 __global__ void __launch_bounds__(256)
-hash_build_kernel(const u64 *__restrict__ key, long long N, HashHeader *hdr) {
+index_count_kernel(const u64 *__restrict__ key, long long N, HashHeader *hdr, DirSlot *dirB, DirSlot *dirA, u32 *slotB, u32 *slotA) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
   const Onv<L> x = load_onv<L>(key + i * L);
@@ -44,22 +65,59 @@ hash_build_kernel(const u64 *__restrict__ key, long long N, HashHeader *hdr) {
     const Onv<L> prev = load_onv<L>(key + (i - 1) * L);
     if (eq_onv<L>(prev, x)) atomicExch(&hdr->has_dup, 1u);
   }
-  const u32 log2_nb = hdr->log2_nb;
-  HashBucket *buckets = reinterpret_cast<HashBucket *>(hdr + 1);
-  const u64 h = hash_onv<L>(x);
-  const u32 tag = hash_tag(h);
-  const u32 mask = (1u << log2_nb) - 1u;
-  u32 b = (u32)(h >> (64 - log2_nb));
+  const u32 lg = hdr->log2_dir;
+  const u32 sb = dir_claim(dirB, lg, hash_beta<L>(x));
+  atomicAdd(&dirB[sb].lg, 1u);
+  slotB[i] = sb;
+  const u32 sa = dir_claim(dirA, lg, hash_alpha<L>(x));
+  atomicAdd(&dirA[sa].lg, 1u);
+  slotA[i] = sa;
+}
+
+// count -> region: buckets = pow2ceil(count) (< 2 count, so the pool of 4N buckets suffices): at most
+// one key per bucket on average, which keeps overflowed buckets (second probes) below 1 %
+__global__ void __launch_bounds__(256) index_carve_kernel(HashHeader *hdr, DirSlot *dirB, DirSlot *dirA) {
+  const u32 slots = 1u << hdr->log2_dir;
+  for (u32 t = blockIdx.x * blockDim.x + threadIdx.x; t < 2 * slots; t += gridDim.x * blockDim.x) {
+    DirSlot *d = t < slots ? dirB + t : dirA + (t - slots);
+    const u32 c = d->lg;
+    if (d->h == kDirEmpty || c == 0) continue;
+    const u32 want = c;
+    u32 lg = 0;
+    while ((1u << lg) < want) ++lg;
+    d->off = atomicAdd(&hdr->cursor, 1u << lg);
+    d->lg = lg;
+  }
+}
+
+__device__ __forceinline__ void region_insert(HashBucket *pool, const DirSlot &d, u64 h2, u32 row) {
+  const u32 mask = (1u << d.lg) - 1u;
+  const u32 tag = hash_tag(h2);
+  u32 b = d.lg ? (u32)(h2 >> (64 - d.lg)) : 0u;
   for (u32 probe = 0; probe <= mask; ++probe) {
+    HashBucket *bk = pool + d.off + b;
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
-      if (atomicCAS(&buckets[b].tag[s], 0u, tag) == 0u) {
-        buckets[b].idx[s] = (u32)i;
+      if (atomicCAS(&bk->tag[s], 0u, tag) == 0u) {
+        bk->idx[s] = row;
         return;
       }
     }
+    atomicAnd(&bk->tag[3], ~1u);  // full: raise the overflow flag and move on
     b = (b + 1) & mask;
   }
+}
+
+template <int L>
+__global__ void __launch_bounds__(256)
+index_fill_kernel(const u64 *__restrict__ key, long long N, const DirSlot *__restrict__ dirB, const DirSlot *__restrict__ dirA,
+                  HashBucket *pool, const u32 *__restrict__ slotB, const u32 *__restrict__ slotA) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const Onv<L> x = load_onv<L>(key + i * L);
+  const u64 ha = hash_alpha<L>(x), hb = hash_beta<L>(x);
+  region_insert(pool, dirB[slotB[i]], ha, (u32)i);  // grouped by beta string, hashed by alpha string
+  region_insert(pool, dirA[slotA[i]], hb, (u32)i);  // grouped by alpha string, hashed by beta string
 }
 
 static inline unsigned grid_for(long long n, int threads, long long cap) {
@@ -68,13 +126,7 @@ static inline unsigned grid_for(long long n, int threads, long long cap) {
   return (unsigned)(want < cap ? want : cap);
 }
 
-static u32 hash_log2_buckets(long long N) {
-  u32 lg = 6;
-  while ((1LL << lg) < N && lg < 31) ++lg;
-  return lg;
-}
-
-long long hash_workspace_bytes(long long N) { return (long long)sizeof(HashHeader) + ((long long)sizeof(HashBucket) << hash_log2_buckets(N)); }
+long long hash_workspace_bytes(long long N) { return index_layout(N).total; }
 
 int launch_lut_classic(const u64 *key, long long N, const u64 *q, long long n, int L, long long *idx, unsigned char *mask,
                        cudaStream_t st) {
@@ -91,45 +143,65 @@ int launch_lut_classic(const u64 *key, long long N, const u64 *q, long long n, i
 }
 
 int launch_hash_build(const u64 *key, long long N, int L, void *ws, long long ws_bytes, cudaStream_t st) {
-  if (N >= (1LL << 32)) {
-    set_error("hash index supports fewer than 2^32 keys (got %lld)", N);
+  if (N >= (1LL << 31)) {
+    set_error("lookup index supports fewer than 2^31 keys (got %lld)", N);
     return 1;
   }
-  const long long need = hash_workspace_bytes(N);
-  if (ws_bytes < need) {
-    set_error("hash workspace too small: %lld < %lld bytes", ws_bytes, need);
+  const IndexLayout l = index_layout(N);
+  if (ws_bytes < l.total) {
+    set_error("index workspace too small: %lld < %lld bytes", ws_bytes, l.total);
     return 4;
   }
-  if (cudaMemsetAsync(ws, 0, (size_t)need, st) != cudaSuccess) return check_launch("hash memset");
-  HashHeader *hdr = reinterpret_cast<HashHeader *>(ws);
-  hash_header_kernel<<<1, 1, 0, st>>>(hdr, hash_log2_buckets(N), (u64)N);
+  char *b = static_cast<char *>(ws);
+  HashHeader *hdr = reinterpret_cast<HashHeader *>(b);
+  DirSlot *dirB = reinterpret_cast<DirSlot *>(b + l.dir_off[0]);
+  DirSlot *dirA = reinterpret_cast<DirSlot *>(b + l.dir_off[1]);
+  HashBucket *pool = reinterpret_cast<HashBucket *>(b + l.pool_off);
+  u32 *slotB = reinterpret_cast<u32 *>(b + l.scratch_off);
+  u32 *slotA = slotB + N;
+  // directories: h = all ones (empty); off / count = garbage-free after the second memset
+  if (cudaMemsetAsync(dirB, 0xff, (size_t)(l.pool_off - l.dir_off[0]), st) != cudaSuccess) return check_launch("index memset");
+  if (cudaMemsetAsync(pool, 0, (size_t)(l.scratch_off - l.pool_off), st) != cudaSuccess) return check_launch("index memset");
+  index_header_kernel<<<1, 1, 0, st>>>(hdr, l.log2_dir, (u64)N, (u32)l.pool_buckets);
   count_launch();
   if (N > 0) {
     const unsigned blocks = (unsigned)((N + 255) / 256);
+    // the count field must start at zero: clear `off`/`lg` of every slot (h stays all ones)
+    // -- done by a strided 2-D memset over the 8 trailing bytes of each 16-byte slot
+    if (cudaMemset2DAsync(reinterpret_cast<char *>(dirB) + 8, sizeof(DirSlot), 0, 8, (size_t)2 << l.log2_dir, st) != cudaSuccess)
+      return check_launch("index memset2d");
     switch (L) {
-      case 1: hash_build_kernel<1><<<blocks, 256, 0, st>>>(key, N, hdr); break;
-      case 2: hash_build_kernel<2><<<blocks, 256, 0, st>>>(key, N, hdr); break;
-      case 3: hash_build_kernel<3><<<blocks, 256, 0, st>>>(key, N, hdr); break;
+      case 1: index_count_kernel<1><<<blocks, 256, 0, st>>>(key, N, hdr, dirB, dirA, slotB, slotA); break;
+      case 2: index_count_kernel<2><<<blocks, 256, 0, st>>>(key, N, hdr, dirB, dirA, slotB, slotA); break;
+      case 3: index_count_kernel<3><<<blocks, 256, 0, st>>>(key, N, hdr, dirB, dirA, slotB, slotA); break;
       default: set_error("unsupported ONV length L=%d", L); return 1;
     }
     count_launch();
+    index_carve_kernel<<<grid_for(2LL << l.log2_dir, 256, 148LL * 8), 256, 0, st>>>(hdr, dirB, dirA);
+    count_launch();
+    switch (L) {
+      case 1: index_fill_kernel<1><<<blocks, 256, 0, st>>>(key, N, dirB, dirA, pool, slotB, slotA); break;
+      case 2: index_fill_kernel<2><<<blocks, 256, 0, st>>>(key, N, dirB, dirA, pool, slotB, slotA); break;
+      default: index_fill_kernel<3><<<blocks, 256, 0, st>>>(key, N, dirB, dirA, pool, slotB, slotA); break;
+    }
+    count_launch();
   }
-  return check_launch("hash_build_kernel");
+  return check_launch("index build");
 }
 
 int launch_lut_hashed(const u64 *key, long long N, const u64 *q, long long n, int L, const void *ws, long long *idx,
                       unsigned char *mask, cudaStream_t st) {
   if (n == 0) return 0;
-  const HashHeader *hdr = reinterpret_cast<const HashHeader *>(ws);
+  const IndexView iv = index_view(ws, N);
   const unsigned blocks = grid_for(n, 256, 148LL * 64);
   switch (L) {
-    case 1: lut_hashed_kernel<1><<<blocks, 256, 0, st>>>(key, N, hdr, q, n, idx, mask); break;
-    case 2: lut_hashed_kernel<2><<<blocks, 256, 0, st>>>(key, N, hdr, q, n, idx, mask); break;
-    case 3: lut_hashed_kernel<3><<<blocks, 256, 0, st>>>(key, N, hdr, q, n, idx, mask); break;
+    case 1: lut_indexed_kernel<1><<<blocks, 256, 0, st>>>(key, N, iv, q, n, idx, mask); break;
+    case 2: lut_indexed_kernel<2><<<blocks, 256, 0, st>>>(key, N, iv, q, n, idx, mask); break;
+    case 3: lut_indexed_kernel<3><<<blocks, 256, 0, st>>>(key, N, iv, q, n, idx, mask); break;
     default: set_error("unsupported ONV length L=%d", L); return 1;
   }
   count_launch();
-  return check_launch("lut_hashed_kernel");
+  return check_launch("lut_indexed_kernel");
 }
 
 }  // namespace pynqs

@@ -2,41 +2,158 @@
 //
 // classic_search: the reference's probe sequence (binary_search_BigInteger,
 // cpp_src/tensor/cpu_tensor.cpp:589-640; BigInteger_device, cuda/kernel.cu:625-650).
-// hashed_search: same answer for a sorted table without duplicates, one 16-byte bucket probe
-// per query instead of ~log2(N) dependent loads.
+//
+// String-grouped index: same answers for a sorted table without duplicates, built for the access
+// pattern of the local-energy path.  An ONV is an (alpha string, beta string) pair (even / odd
+// bits).  The connected determinants of one sample that a warp probes together share one of the
+// two strings (alpha-beta doubles with the same beta excitation, alpha-alpha doubles and alpha
+// singles share the beta string; beta-beta doubles and beta singles share the alpha string), so
+// the index groups the keys twice:
+//   directory[B]: hash(beta string)  -> region of the keys with that beta string, hashed by alpha string
+//   directory[A]: hash(alpha string) -> region of the keys with that alpha string, hashed by beta string
+// A region is a power-of-two run of 32-byte buckets {tag[4], idx[4]} (tag = low 32 bits of the
+// other string's hash, idx = row in the sorted table).  The 32 probes of a warp land in ONE
+// region (a few 128-byte lines) instead of 32 random lines of a flat table, and whole groups of
+// rows are skipped when their string is absent from the directory.  Every hit is verified
+// against the key table, so hash collisions (even of the 64-bit directory keys, which merely
+// merge two groups) cannot change a result.
 #pragma once
 #include "common.cuh"
 
 namespace pynqs {
 
-// workspace layout: HashHeader (256 B) | buckets[nb] of 32 B {tag[4], idx[4]}
+constexpr u64 kDirEmpty = ~0ull;
+
 struct HashHeader {
-  u32 log2_nb;
-  u32 has_dup;  // set by the build when two adjacent sorted keys are equal
+  u32 log2_dir;  // directory slots (each of the two directories)
+  u32 has_dup;   // set by the build when two adjacent sorted keys are equal
   u64 n_keys;
-  u32 pad[60];
+  u32 cursor;    // bump allocator over the shared bucket pool
+  u32 pool_buckets;
+  u32 pad[58];
 };
 static_assert(sizeof(HashHeader) == 256, "header is 256 bytes");
 
-struct HashBucket {
+struct __align__(16) DirSlot {
+  u64 h;    // 64-bit hash of the grouping string (kDirEmpty = free)
+  u32 off;  // first bucket of the region in the pool
+  u32 lg;   // log2(buckets of the region); during the build: number of keys of the group
+};
+
+// tag = low 32 bits of the string hash with bits 0 and 1 forced to 1 (never 0 = empty).  Slots fill
+// from 0 upwards.  When a key finds its bucket full and moves on, it clears bit 0 of tag[3]: that is
+// the bucket's OVERFLOW flag, the only case in which a probe has to look at the next bucket.
+struct __align__(16) HashBucket {
   u32 tag[4];
   u32 idx[4];
 };
 
-template <int L>
-__device__ __forceinline__ u64 hash_onv(const Onv<L> &x) {
-  u64 h = x.w[0] * 0x9E3779B97F4A7C15ull;
-#pragma unroll
-  for (int i = 1; i < L; ++i) h = (h ^ (h >> 32) ^ x.w[i]) * 0xD6E8FEB86659FD93ull;
-  h ^= h >> 32;
-  h *= 0xD6E8FEB86659FD93ull;
-  h ^= h >> 32;
-  return h;
+// workspace: header | dir[B] | dir[A] | bucket pool (4N + 2 buckets) | slot scratch (2N u32)
+struct IndexLayout {
+  u32 log2_dir;
+  long long dir_off[2], pool_off, scratch_off, total;
+  long long pool_buckets;
+};
+
+__host__ __device__ inline IndexLayout index_layout(long long N) {
+  IndexLayout l;
+  u32 lg = 6;
+  while ((1LL << lg) < 2 * N && lg < 31) ++lg;
+  l.log2_dir = lg;
+  l.dir_off[0] = (long long)sizeof(HashHeader);
+  l.dir_off[1] = l.dir_off[0] + ((long long)sizeof(DirSlot) << lg);
+  l.pool_off = l.dir_off[1] + ((long long)sizeof(DirSlot) << lg);
+  l.pool_buckets = 4 * N + 2;  // each of the two groupings needs < 2N buckets (<= 1 key per bucket on average)
+  l.scratch_off = l.pool_off + l.pool_buckets * (long long)sizeof(HashBucket);
+  l.total = l.scratch_off + 2 * N * 4 + 16;
+  return l;
 }
 
-__device__ __forceinline__ u32 hash_tag(u64 h) {
-  const u32 t = (u32)h;
-  return t ? t : 1u;
+struct IndexView {
+  const HashHeader *hdr;
+  const DirSlot *dir[2];  // [0] grouped by beta string, [1] grouped by alpha string
+  const HashBucket *pool;
+  u32 log2_dir;
+};
+
+__host__ __device__ inline IndexView index_view(const void *ws, long long N) {
+  const IndexLayout l = index_layout(N);
+  const char *b = reinterpret_cast<const char *>(ws);
+  IndexView v;
+  v.hdr = reinterpret_cast<const HashHeader *>(b);
+  v.dir[0] = reinterpret_cast<const DirSlot *>(b + l.dir_off[0]);
+  v.dir[1] = reinterpret_cast<const DirSlot *>(b + l.dir_off[1]);
+  v.pool = reinterpret_cast<const HashBucket *>(b + l.pool_off);
+  v.log2_dir = l.log2_dir;
+  return v;
+}
+
+// 64-bit hash of one spin string: the words of the ONV masked to the even (which = 1, alpha) or
+// odd (which = 0, beta) bits.  Never returns kDirEmpty.
+template <int L>
+__device__ __forceinline__ u64 hash_string(const Onv<L> &x, u64 spin_mask) {
+  u64 h = (x.w[0] & spin_mask) * 0x9E3779B97F4A7C15ull;
+#pragma unroll
+  for (int i = 1; i < L; ++i) h = (h ^ (h >> 29) ^ (x.w[i] & spin_mask)) * 0xBF58476D1CE4E5B9ull;
+  h ^= h >> 32;
+  h *= 0xD6E8FEB86659FD93ull;
+  h ^= h >> 29;
+  return h == kDirEmpty ? kDirEmpty - 1 : h;
+}
+template <int L>
+__device__ __forceinline__ u64 hash_alpha(const Onv<L> &x) { return hash_string<L>(x, kEven); }
+template <int L>
+__device__ __forceinline__ u64 hash_beta(const Onv<L> &x) { return hash_string<L>(x, kOdd); }
+
+__device__ __forceinline__ u32 hash_tag(u64 h) { return (u32)h | 3u; }
+__device__ __forceinline__ bool tags_match(const uint4 &t, u32 tag) {
+  return t.x == tag || t.y == tag || t.z == tag || (t.w | 1u) == tag;
+}
+__device__ __forceinline__ bool bucket_overflowed(const uint4 &t) { return t.w != 0u && !(t.w & 1u); }
+
+// region descriptor packed in 64 bits: off | lg << 32; kNoRegion when the group does not exist
+constexpr u64 kNoRegion = ~0ull;
+
+__device__ __forceinline__ u64 dir_find(const DirSlot *__restrict__ dir, u32 log2_dir, u64 h) {
+  const u32 mask = (1u << log2_dir) - 1u;
+  u32 s = (u32)(h >> (64 - log2_dir));
+  for (u32 probe = 0; probe <= mask; ++probe) {
+    const uint4 e = __ldg(reinterpret_cast<const uint4 *>(dir + s));
+    const u64 eh = (u64)e.x | ((u64)e.y << 32);
+    if (eh == h) return (u64)e.z | ((u64)e.w << 32);
+    if (eh == kDirEmpty) return kNoRegion;
+    s = (s + 1) & mask;
+  }
+  return kNoRegion;
+}
+
+// probe the region `desc` for the string hash h2; make_key() builds the query only when a tag matches
+template <int L, typename MakeKey>
+__device__ __forceinline__ long long region_probe(const u64 *__restrict__ key, const HashBucket *__restrict__ pool, u64 desc,
+                                                  u64 h2, MakeKey make_key) {
+  const u32 off = (u32)desc, lg = (u32)(desc >> 32);
+  const u32 mask = (1u << lg) - 1u;
+  const u32 tag = hash_tag(h2);
+  u32 b = lg ? (u32)(h2 >> (64 - lg)) : 0u;
+  for (u32 probe = 0; probe <= mask; ++probe) {
+    const HashBucket *bk = pool + off + b;
+    const uint4 t = __ldg(reinterpret_cast<const uint4 *>(bk->tag));
+    if (tags_match(t, tag)) {
+      const Onv<L> q = make_key();
+      const u32 tg[4] = {t.x, t.y, t.z, t.w | 1u};
+#pragma unroll
+      for (int s = 0; s < 4; ++s) {
+        if (tg[s] == tag) {
+          const u32 id = __ldg(&bk->idx[s]);
+          const Onv<L> e = load_onv<L>(key + (long long)id * L);
+          if (eq_onv<L>(e, q)) return (long long)id;
+        }
+      }
+    }
+    if (!bucket_overflowed(t)) return -1;
+    b = (b + 1) & mask;
+  }
+  return -1;
 }
 
 template <int L>
@@ -53,33 +170,12 @@ __device__ __forceinline__ long long classic_search(const u64 *__restrict__ key,
   return -1;
 }
 
+// full lookup of an arbitrary ONV through the beta-grouped directory (tables without duplicates)
 template <int L>
-__device__ __forceinline__ long long hashed_search(const u64 *__restrict__ key, long long N, const HashHeader *__restrict__ hdr,
-                                                   const Onv<L> &q) {
-  if (hdr->has_dup) return classic_search<L>(key, N, q);
-  const u32 log2_nb = hdr->log2_nb;
-  const HashBucket *__restrict__ buckets = reinterpret_cast<const HashBucket *>(hdr + 1);
-  const u64 h = hash_onv<L>(q);
-  const u32 tag = hash_tag(h);
-  const u32 mask = (1u << log2_nb) - 1u;
-  u32 b = (u32)(h >> (64 - log2_nb));
-  for (u32 probe = 0; probe <= mask; ++probe) {
-    const uint4 t = __ldg(reinterpret_cast<const uint4 *>(buckets[b].tag));
-    const u32 tg[4] = {t.x, t.y, t.z, t.w};
-    bool open = false;
-#pragma unroll
-    for (int s = 0; s < 4; ++s) {
-      if (tg[s] == tag) {
-        const u32 id = __ldg(&buckets[b].idx[s]);
-        const Onv<L> e = load_onv<L>(key + (long long)id * L);
-        if (eq_onv<L>(e, q)) return (long long)id;
-      }
-      open |= (tg[s] == 0u);
-    }
-    if (open) return -1;
-    b = (b + 1) & mask;
-  }
-  return -1;
+__device__ __forceinline__ long long indexed_search(const u64 *__restrict__ key, const IndexView &iv, const Onv<L> &q) {
+  const u64 desc = dir_find(iv.dir[0], iv.log2_dir, hash_beta<L>(q));
+  if (desc == kNoRegion) return -1;
+  return region_probe<L>(key, iv.pool, desc, hash_alpha<L>(q), [&]() { return q; });
 }
 
 }  // namespace pynqs
