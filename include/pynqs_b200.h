@@ -111,14 +111,13 @@ int pynqs_lut_hashed(const uint8_t *key, int64_t N, const uint8_t *onv, int64_t 
  * never materialising comb / Hmat:  for each sample x, psi0 = table value of x (0 if absent),
  *   eloc = sum over x' in {x} U SD(x) found in the table of (psi(x') / psi0) * <x|H|x'>.
  * psi: double[N] (psi_complex == 0) or interleaved complex128[N]; eloc / psi0 likewise [n].
- * scratch: pynqs_eloc_scratch_bytes(n, ...) bytes.  h1e/h2e are float64; prep_ws = prepared
- * float64 integrals of h2e (pynqs_prepare_integrals) or NULL (slower hit evaluation, same results).
+ * scratch: pynqs_eloc_scratch_bytes(n, ...) bytes.  h1e/h2e are the packed float64 arrays.
  * hash_ws must have been built by pynqs_hash_build for exactly this key table. */
 int pynqs_eloc_scratch_bytes(int64_t n, int sorb, int noA, int noB, int psi_complex, int64_t *bytes);
-int pynqs_eloc_sample_space(const uint8_t *bra, int64_t n, const double *h1e, const double *h2e,
-                            const void *prep_ws, int sorb, int nele, int noA, int noB, const uint8_t *key,
-                            const void *psi, int psi_complex, int64_t N, const void *hash_ws, void *scratch,
-                            int64_t scratch_bytes, void *eloc, void *psi0, void *stream);
+int pynqs_eloc_sample_space(const uint8_t *bra, int64_t n, const double *h1e, const double *h2e, int sorb,
+                            int nele, int noA, int noB, const uint8_t *key, const void *psi, int psi_complex,
+                            int64_t N, const void *hash_ws, void *scratch, int64_t scratch_bytes, void *eloc,
+                            void *psi0, void *stream);
 
 /* number of kernel launches issued by this library in this process (bench.py's gpu_launches). */
 int64_t pynqs_launch_count(void);

@@ -351,7 +351,6 @@ def wavefunction_lut(bra_key: Tensor, onv: Tensor, sorb: int, little_endian: boo
 def eloc_sample_space(
     bra: Tensor, h1e: Tensor, h2e: Tensor, sorb: int, nele: int, noA: int, noB: int,
     bra_key: Tensor, wf_value: Tensor, hash_index: HashIndex | None = None,
-    prepared: "PreparedIntegrals | None | bool" = None,
 ) -> Tuple[Tensor, Tensor]:
     """Additive op: the whole sample-space local energy of vmc/energy/eloc.py:326-397 in one pass.
     Returns (eloc [n], psi0 [n]) in wf_value's dtype (float64 or complex128).  bra_key must be the
@@ -375,11 +374,6 @@ def eloc_sample_space(
         return eloc, psi0
     if hash_index is None:
         hash_index = _cached_hash(bra_key)
-    if prepared is None:
-        prepared = _cached_prep(h2e, sorb)
-    prep_ptr = prepared.workspace.data_ptr() if prepared else None
-    if prepared and (prepared.sorb != sorb or prepared.dtype != torch.float64):
-        raise ValueError("prepared integrals do not match sorb / dtype")
     lib = _lib.load()
     nbytes = _lib.ctypes.c_int64()
     _lib.check(lib.pynqs_eloc_scratch_bytes(i64(n), int(sorb), int(noA), int(noB), cplx, _lib.ctypes.byref(nbytes)))
@@ -387,7 +381,7 @@ def eloc_sample_space(
     with torch.cuda.device(dev):
         _lib.check(
             lib.pynqs_eloc_sample_space(
-                vp(bra.data_ptr()), i64(n), vp(h1e.data_ptr()), vp(h2e.data_ptr()), vp(prep_ptr), int(sorb), int(nele), int(noA), int(noB),
+                vp(bra.data_ptr()), i64(n), vp(h1e.data_ptr()), vp(h2e.data_ptr()), int(sorb), int(nele), int(noA), int(noB),
                 vp(bra_key.data_ptr()), vp(wf_value.data_ptr()), cplx, i64(N), vp(hash_index.workspace.data_ptr()),
                 vp(scratch.data_ptr()), i64(nbytes.value), vp(eloc.data_ptr()), vp(psi0.data_ptr()), _stream(dev),
             )

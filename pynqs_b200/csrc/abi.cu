@@ -47,7 +47,7 @@ long long hash_workspace_bytes(long long);
 int launch_hash_build(const u64 *, long long, int, void *, long long, cudaStream_t);
 int launch_lut_hashed(const u64 *, long long, const u64 *, long long, int, const void *, long long *, unsigned char *, cudaStream_t);
 long long eloc_scratch_bytes(long long, int, int);
-int launch_eloc(const u64 *, long long, const double *, const double *, const void *, const u64 *, const double *, int, long long,
+int launch_eloc(const u64 *, long long, const double *, const double *, const u64 *, const double *, int, long long,
                 const void *, void *, long long, double *, double *, const ExcGeom &, cudaStream_t);
 int launch_onv_to_tensor(const u64 *, void *, int, long long, int, cudaStream_t);
 int launch_tensor_to_onv(const unsigned char *, unsigned char *, long long, int, cudaStream_t);
@@ -243,15 +243,15 @@ int pynqs_eloc_scratch_bytes(int64_t n, int sorb, int noA, int noB, int psi_comp
   return 0;
 }
 
-int pynqs_eloc_sample_space(const uint8_t *bra, int64_t n, const double *h1e, const double *h2e, const void *prep_ws,
-                            int sorb, int nele, int noA, int noB, const uint8_t *key, const void *psi, int psi_complex, int64_t N,
+int pynqs_eloc_sample_space(const uint8_t *bra, int64_t n, const double *h1e, const double *h2e, int sorb, int nele,
+                            int noA, int noB, const uint8_t *key, const void *psi, int psi_complex, int64_t N,
                             const void *hash_ws, void *scratch, int64_t scratch_bytes, void *eloc, void *psi0,
                             void *stream) {
   if (int rc = check_geometry(sorb, nele, noA, noB)) return rc;
   long long nsd;
   if (int rc = num_sd_checked(sorb, noA, noB, &nsd)) return rc;
   const ExcGeom g = make_geom(sorb, nele, noA, noB);
-  return launch_eloc(reinterpret_cast<const u64 *>(bra), n, h1e, h2e, prep_ws, reinterpret_cast<const u64 *>(key),
+  return launch_eloc(reinterpret_cast<const u64 *>(bra), n, h1e, h2e, reinterpret_cast<const u64 *>(key),
                      (const double *)psi, psi_complex, N, hash_ws, scratch, scratch_bytes, (double *)eloc, (double *)psi0, g,
                      (cudaStream_t)stream);
 }

@@ -90,20 +90,20 @@ __global__ void __launch_bounds__(256) index_carve_kernel(HashHeader *hdr, DirSl
   }
 }
 
-__device__ __forceinline__ void region_insert(HashBucket *pool, const DirSlot &d, u64 h2, u32 row) {
+__device__ __forceinline__ void region_insert(u32 *tags, u32 *rows, const DirSlot &d, u64 h2, u32 row) {
   const u32 mask = (1u << d.lg) - 1u;
   const u32 tag = hash_tag(h2);
   u32 b = d.lg ? (u32)(h2 >> (64 - d.lg)) : 0u;
   for (u32 probe = 0; probe <= mask; ++probe) {
-    HashBucket *bk = pool + d.off + b;
+    const size_t base = 4 * (size_t)(d.off + b);
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
-      if (atomicCAS(&bk->tag[s], 0u, tag) == 0u) {
-        bk->idx[s] = row;
+      if (atomicCAS(&tags[base + s], 0u, tag) == 0u) {
+        rows[base + s] = row;
         return;
       }
     }
-    atomicAnd(&bk->tag[3], ~1u);  // full: raise the overflow flag and move on
+    atomicAnd(&tags[base + 3], ~1u);  // full: raise the overflow flag and move on
     b = (b + 1) & mask;
   }
 }
@@ -111,13 +111,13 @@ __device__ __forceinline__ void region_insert(HashBucket *pool, const DirSlot &d
 template <int L>
 __global__ void __launch_bounds__(256)
 index_fill_kernel(const u64 *__restrict__ key, long long N, const DirSlot *__restrict__ dirB, const DirSlot *__restrict__ dirA,
-                  HashBucket *pool, const u32 *__restrict__ slotB, const u32 *__restrict__ slotA) {
+                  u32 *tags, u32 *rows, const u32 *__restrict__ slotB, const u32 *__restrict__ slotA) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
   const Onv<L> x = load_onv<L>(key + i * L);
   const u64 ha = hash_alpha<L>(x), hb = hash_beta<L>(x);
-  region_insert(pool, dirB[slotB[i]], ha, (u32)i);  // grouped by beta string, hashed by alpha string
-  region_insert(pool, dirA[slotA[i]], hb, (u32)i);  // grouped by alpha string, hashed by beta string
+  region_insert(tags, rows, dirB[slotB[i]], ha, (u32)i);  // grouped by beta string, hashed by alpha string
+  region_insert(tags, rows, dirA[slotA[i]], hb, (u32)i);  // grouped by alpha string, hashed by beta string
 }
 
 static inline unsigned grid_for(long long n, int threads, long long cap) {
@@ -156,12 +156,13 @@ int launch_hash_build(const u64 *key, long long N, int L, void *ws, long long ws
   HashHeader *hdr = reinterpret_cast<HashHeader *>(b);
   DirSlot *dirB = reinterpret_cast<DirSlot *>(b + l.dir_off[0]);
   DirSlot *dirA = reinterpret_cast<DirSlot *>(b + l.dir_off[1]);
-  HashBucket *pool = reinterpret_cast<HashBucket *>(b + l.pool_off);
+  u32 *pool = reinterpret_cast<u32 *>(b + l.pool_off);
+  u32 *rows = reinterpret_cast<u32 *>(b + l.idx_off);
   u32 *slotB = reinterpret_cast<u32 *>(b + l.scratch_off);
   u32 *slotA = slotB + N;
   // directories: h = all ones (empty); off / count = garbage-free after the second memset
   if (cudaMemsetAsync(dirB, 0xff, (size_t)(l.pool_off - l.dir_off[0]), st) != cudaSuccess) return check_launch("index memset");
-  if (cudaMemsetAsync(pool, 0, (size_t)(l.scratch_off - l.pool_off), st) != cudaSuccess) return check_launch("index memset");
+  if (cudaMemsetAsync(pool, 0, (size_t)(l.idx_off - l.pool_off), st) != cudaSuccess) return check_launch("index memset");
   index_header_kernel<<<1, 1, 0, st>>>(hdr, l.log2_dir, (u64)N, (u32)l.pool_buckets);
   count_launch();
   if (N > 0) {
@@ -180,9 +181,9 @@ int launch_hash_build(const u64 *key, long long N, int L, void *ws, long long ws
     index_carve_kernel<<<grid_for(2LL << l.log2_dir, 256, 148LL * 8), 256, 0, st>>>(hdr, dirB, dirA);
     count_launch();
     switch (L) {
-      case 1: index_fill_kernel<1><<<blocks, 256, 0, st>>>(key, N, dirB, dirA, pool, slotB, slotA); break;
-      case 2: index_fill_kernel<2><<<blocks, 256, 0, st>>>(key, N, dirB, dirA, pool, slotB, slotA); break;
-      default: index_fill_kernel<3><<<blocks, 256, 0, st>>>(key, N, dirB, dirA, pool, slotB, slotA); break;
+      case 1: index_fill_kernel<1><<<blocks, 256, 0, st>>>(key, N, dirB, dirA, pool, rows, slotB, slotA); break;
+      case 2: index_fill_kernel<2><<<blocks, 256, 0, st>>>(key, N, dirB, dirA, pool, rows, slotB, slotA); break;
+      default: index_fill_kernel<3><<<blocks, 256, 0, st>>>(key, N, dirB, dirA, pool, rows, slotB, slotA); break;
     }
     count_launch();
   }

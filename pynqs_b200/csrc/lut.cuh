@@ -11,7 +11,7 @@
 // the index groups the keys twice:
 //   directory[B]: hash(beta string)  -> region of the keys with that beta string, hashed by alpha string
 //   directory[A]: hash(alpha string) -> region of the keys with that alpha string, hashed by beta string
-// A region is a power-of-two run of 32-byte buckets {tag[4], idx[4]} (tag = low 32 bits of the
+// A region is a power-of-two run of buckets {tag[4]} + {idx[4]} (tag = low 32 bits of the
 // other string's hash, idx = row in the sorted table).  The 32 probes of a warp land in ONE
 // region (a few 128-byte lines) instead of 32 random lines of a flat table, and whole groups of
 // rows are skipped when their string is absent from the directory.  Every hit is verified
@@ -43,15 +43,15 @@ struct __align__(16) DirSlot {
 // tag = low 32 bits of the string hash with bits 0 and 1 forced to 1 (never 0 = empty).  Slots fill
 // from 0 upwards.  When a key finds its bucket full and moves on, it clears bit 0 of tag[3]: that is
 // the bucket's OVERFLOW flag, the only case in which a probe has to look at the next bucket.
-struct __align__(16) HashBucket {
-  u32 tag[4];
-  u32 idx[4];
-};
+// Tags and rows live in two parallel arrays (uint4 per bucket each): the fast path of a probe reads
+// only the 16 tag bytes, so the buckets of a region are packed 8 per 128-byte line.
+typedef uint4 TagBucket;  // tag[4]
+typedef uint4 IdxBucket;  // idx[4]
 
-// workspace: header | dir[B] | dir[A] | bucket pool (4N + 2 buckets) | slot scratch (2N u32)
+// workspace: header | dir[B] | dir[A] | tag pool (4N + 2 buckets) | idx pool | slot scratch (2N u32)
 struct IndexLayout {
   u32 log2_dir;
-  long long dir_off[2], pool_off, scratch_off, total;
+  long long dir_off[2], pool_off, idx_off, scratch_off, total;
   long long pool_buckets;
 };
 
@@ -64,7 +64,8 @@ __host__ __device__ inline IndexLayout index_layout(long long N) {
   l.dir_off[1] = l.dir_off[0] + ((long long)sizeof(DirSlot) << lg);
   l.pool_off = l.dir_off[1] + ((long long)sizeof(DirSlot) << lg);
   l.pool_buckets = 4 * N + 2;  // each of the two groupings needs < 2N buckets (<= 1 key per bucket on average)
-  l.scratch_off = l.pool_off + l.pool_buckets * (long long)sizeof(HashBucket);
+  l.idx_off = l.pool_off + l.pool_buckets * (long long)sizeof(TagBucket);
+  l.scratch_off = l.idx_off + l.pool_buckets * (long long)sizeof(IdxBucket);
   l.total = l.scratch_off + 2 * N * 4 + 16;
   return l;
 }
@@ -72,7 +73,8 @@ __host__ __device__ inline IndexLayout index_layout(long long N) {
 struct IndexView {
   const HashHeader *hdr;
   const DirSlot *dir[2];  // [0] grouped by beta string, [1] grouped by alpha string
-  const HashBucket *pool;
+  const TagBucket *pool;  // tags
+  const IdxBucket *rows;  // table rows, same indexing
   u32 log2_dir;
 };
 
@@ -83,7 +85,8 @@ __host__ __device__ inline IndexView index_view(const void *ws, long long N) {
   v.hdr = reinterpret_cast<const HashHeader *>(b);
   v.dir[0] = reinterpret_cast<const DirSlot *>(b + l.dir_off[0]);
   v.dir[1] = reinterpret_cast<const DirSlot *>(b + l.dir_off[1]);
-  v.pool = reinterpret_cast<const HashBucket *>(b + l.pool_off);
+  v.pool = reinterpret_cast<const TagBucket *>(b + l.pool_off);
+  v.rows = reinterpret_cast<const IdxBucket *>(b + l.idx_off);
   v.log2_dir = l.log2_dir;
   return v;
 }
@@ -129,24 +132,23 @@ __device__ __forceinline__ u64 dir_find(const DirSlot *__restrict__ dir, u32 log
 
 // probe the region `desc` for the string hash h2; make_key() builds the query only when a tag matches
 template <int L, typename MakeKey>
-__device__ __forceinline__ long long region_probe(const u64 *__restrict__ key, const HashBucket *__restrict__ pool, u64 desc,
-                                                  u64 h2, MakeKey make_key) {
+__device__ __forceinline__ long long region_probe(const u64 *__restrict__ key, const IndexView &iv, u64 desc, u64 h2,
+                                                  MakeKey make_key) {
   const u32 off = (u32)desc, lg = (u32)(desc >> 32);
   const u32 mask = (1u << lg) - 1u;
   const u32 tag = hash_tag(h2);
   u32 b = lg ? (u32)(h2 >> (64 - lg)) : 0u;
   for (u32 probe = 0; probe <= mask; ++probe) {
-    const HashBucket *bk = pool + off + b;
-    const uint4 t = __ldg(reinterpret_cast<const uint4 *>(bk->tag));
+    const uint4 t = __ldg(iv.pool + off + b);
     if (tags_match(t, tag)) {
       const Onv<L> q = make_key();
-      const u32 tg[4] = {t.x, t.y, t.z, t.w | 1u};
+      const uint4 ids = __ldg(iv.rows + off + b);
+      const u32 tg[4] = {t.x, t.y, t.z, t.w | 1u}, id[4] = {ids.x, ids.y, ids.z, ids.w};
 #pragma unroll
       for (int s = 0; s < 4; ++s) {
         if (tg[s] == tag) {
-          const u32 id = __ldg(&bk->idx[s]);
-          const Onv<L> e = load_onv<L>(key + (long long)id * L);
-          if (eq_onv<L>(e, q)) return (long long)id;
+          const Onv<L> e = load_onv<L>(key + (long long)id[s] * L);
+          if (eq_onv<L>(e, q)) return (long long)id[s];
         }
       }
     }
@@ -175,7 +177,7 @@ template <int L>
 __device__ __forceinline__ long long indexed_search(const u64 *__restrict__ key, const IndexView &iv, const Onv<L> &q) {
   const u64 desc = dir_find(iv.dir[0], iv.log2_dir, hash_beta<L>(q));
   if (desc == kNoRegion) return -1;
-  return region_probe<L>(key, iv.pool, desc, hash_alpha<L>(q), [&]() { return q; });
+  return region_probe<L>(key, iv, desc, hash_alpha<L>(q), [&]() { return q; });
 }
 
 }  // namespace pynqs
