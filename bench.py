@@ -311,12 +311,15 @@ def run_ours(args):
     k_n = kern[0][1]
     peak, peak_src = hbm_peak_gbs()
     achieved = B * k_n / (k_ms * 1e-3) / 1e9
-    roof = {"bound": "hbm", "kernel": "eloc_kernel<1,real> (+diag_kernel)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-            "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-            "algorithmic_bytes_per_sample": B, "samples_per_launch": k_n, "kernel_ms": k_ms,
-            "note": "one-pass kernel: algorithmic bytes are the API-path (fused+lut) bytes it replaces, SURVEY.md 8(d); "
-                    "its real DRAM traffic is ~16 B/sample, see profiles/"}
-
+    prof = load_profile_numbers()
+    roof = {"bound": "hbm", "kernel": "eloc_filter_kernel<1> (+ eloc_eval_kernel, diag_kernel): one-pass sample-space E_loc",
+            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": prof.get("eloc_dram_bytes_per_sample"), "traffic_unit": "DRAM bytes per sample (ncu, profiles/)",
+            "peak_source": peak_src, "algorithmic_bytes_per_sample": B, "samples_per_launch": k_n, "kernel_ms": k_ms,
+            "note": "equivalent-bytes roofline per SURVEY.md 8(d): the one-pass kernels never write comb/Hmat/idx, so "
+                    "'achieved' = API-path bytes (fused + lut, 259.9 KB/sample) / time and may exceed the HBM peak; their real "
+                    "bound is L1/LSU wavefronts + issue slots (profiles/). The kernels that really move those bytes are in "
+                    "'roofline_hbm_kernels'."}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -337,7 +340,7 @@ def run_ours(args):
         "energy": {"mean": st["mean"], "var": st["var"], "mean_e2e": st2["mean"]},
     }
     if world == 1 and not args.no_api_path:
-        line["api_path"] = time_api_path(ops, dev, d_keys, d_psi, h1e, h2e, M, peak)
+        line["roofline_hbm_kernels"] = time_api_path(ops, dev, d_keys, d_psi, h1e, h2e, M, peak, prof)
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = time_cpu_baseline(keys_np, psi_np, h1e_np, h2e_np)
     else:
@@ -347,17 +350,29 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def time_api_path(ops, dev, d_keys, d_psi, h1e, h2e, M, peak, chunk=32768, reps=5):
-    """The materialising reference-API kernels on one chunk: real HBM writers, reported beside the headline."""
+def load_profile_numbers():
+    """ncu-derived per-launch DRAM traffic of the committed profile (profiles/r01/traffic.json), if present."""
+    path = os.path.join(ROOT, "profiles", "r01", "traffic.json")
+    try:
+        return json.load(open(path))
+    except Exception:
+        return {}
+
+
+def time_api_path(ops, dev, d_keys, d_psi, h1e, h2e, M, peak, prof, chunk=32768, reps=7):
+    """The materialising reference-API kernels on one chunk: the real HBM movers of the hot path.
+    Outputs are pre-allocated by torch inside the call (caching allocator, no cudaMalloc after warm-up);
+    2.06 GB comb + 2.06 GB Hmat per call exceed L2, so no flush is needed between repetitions."""
     import torch
 
     from pynqs_b200.lut import WavefunctionLUT
 
     lut = WavefunctionLUT(d_keys, d_psi, SORB, dev, rank=0, world_size=1)
     x = lut.bra_key[:chunk]
+    prep = ops.PreparedIntegrals(h2e, SORB)
 
     def t(fn):
-        for _ in range(2):
+        for _ in range(3):
             out = fn()
         ts = []
         for _ in range(reps):
@@ -369,16 +384,18 @@ def time_api_path(ops, dev, d_keys, d_psi, h1e, h2e, M, peak, chunk=32768, reps=
             ts.append(a.elapsed_time(b))
         return statistics.median(ts), out
 
-    f_ms, (comb, hmat) = t(lambda: ops.get_comb_hij_fused(x, h1e, h2e, SORB, NELE, NOA, NOB))
+    f_ms, (comb, hmat) = t(lambda: ops.get_comb_hij_fused(x, h1e, h2e, SORB, NELE, NOA, NOB, prepared=prep))
     flat = comb.view(-1, 8)
     l_ms, _ = t(lambda: ops.wavefunction_lut(lut.bra_key, flat, SORB, hash_index=lut.hash_index))
     fb, lb = (16 * M + 8) * chunk, 17 * M * chunk
-    return {
-        "chunk_samples": chunk,
-        "get_comb_hij_fused": {"ms": f_ms, "samples_per_s": chunk / f_ms * 1e3, "GBps": fb / f_ms / 1e6, "frac_hbm": fb / f_ms / 1e6 / peak},
-        "wavefunction_lut": {"ms": l_ms, "samples_per_s": chunk / l_ms * 1e3, "GBps": lb / l_ms / 1e6, "frac_hbm": lb / l_ms / 1e6 / peak},
-        "note": "includes torch output allocation; outputs (comb 2.06 GB + Hmat 2.06 GB per chunk) exceed L2",
-    }
+    return [
+        {"bound": "hbm", "kernel": "enumerate_kernel<1,double,true> (+diag_kernel) = get_comb_hij_fused", "achieved": fb / f_ms / 1e6,
+         "peak": peak, "unit": "GB/s", "frac": fb / f_ms / 1e6 / peak, "traffic": prof.get("enumerate_dram_bytes_per_launch"),
+         "algorithmic_bytes_per_launch": fb, "samples_per_launch": chunk, "ms": f_ms, "samples_per_s": chunk / f_ms * 1e3},
+        {"bound": "hbm", "kernel": "lut_indexed_kernel<1> = wavefunction_lut", "achieved": lb / l_ms / 1e6, "peak": peak,
+         "unit": "GB/s", "frac": lb / l_ms / 1e6 / peak, "traffic": prof.get("lut_dram_bytes_per_launch"),
+         "algorithmic_bytes_per_launch": lb, "samples_per_launch": chunk, "ms": l_ms, "samples_per_s": chunk / l_ms * 1e3},
+    ]
 
 
 def main():

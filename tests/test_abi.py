@@ -83,3 +83,21 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in txt.replace("# oracle", ""), f"{f} mentions the oracle"
+
+
+def test_libs_c_extension_exposes_the_reference_names():
+    """Every function / attribute of the reference's libs/C_extension.pyi (minus the experimental CUDA
+    hash-table API, whose import is try/except-guarded in the reference, utils/public_function.py:24-30)."""
+    import libs.C_extension as ext
+
+    names = ["tensor_to_onv", "onv_to_tensor", "get_comb_tensor", "get_hij_torch", "get_comb_hij_fused", "MCMC_sample",
+             "spin_flip_rand", "mps_vbatch", "permute_sgn", "convert_sites", "merge_rank_sample", "constrain_make_charts",
+             "wavefunction_lut", "check_sorb", "compress_h1e_h2e", "decompress_h1e_h2e", "MAX_SORB", "MAX_SORB_LEN", "MAX_NELE"]
+    for n in names:
+        assert hasattr(ext, n), n
+    import inspect
+
+    assert list(inspect.signature(ext.get_comb_hij_fused).parameters)[:7] == ["bra", "h1e", "h2e", "sorb", "nele", "noA", "noB"]
+    assert list(inspect.signature(ext.get_comb_tensor).parameters) == ["bra", "sorb", "nele", "noA", "noB", "flag_bit"]
+    assert list(inspect.signature(ext.get_hij_torch).parameters) == ["bra", "ket", "h1e", "h2e", "sorb", "nele"]
+    assert list(inspect.signature(ext.wavefunction_lut).parameters)[:4] == ["bra_key", "onv", "sorb", "little_endian"]
