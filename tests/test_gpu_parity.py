@@ -242,6 +242,57 @@ def test_eloc_sample_missing_from_table_gives_nan_like_reference():
     assert (psi_x[10:] == 0).all()
 
 
+def test_eloc_dense_table_overflows_the_candidate_queues():
+    """Full 24-spin-orbital space (6a6b, 853 776 keys): EVERY connected determinant is in the table, so
+    the per-warp candidate queues of the filter kernel overflow and the eval kernel redoes the rows in
+    full -- the result must still equal the oracle and the three-call path."""
+    sorb, noA, noB, nele = 24, 6, 6, 12
+    import itertools
+
+    strings = [sum(1 << (2 * k) for k in c) for c in itertools.combinations(range(12), 6)]
+    a = np.array(strings, dtype=np.uint64)
+    keys64 = (a[:, None] | (a[None, :] << np.uint64(1))).reshape(-1)          # alpha on even, beta on odd bits
+    keys = keys64.view(np.uint8).reshape(-1, 8)
+    assert keys.shape[0] == 853776
+    rng = np.random.default_rng(5)
+    keys = keys[rng.permutation(keys.shape[0])]
+    psi = S.random_psi(keys.shape[0], seed=6)
+    h1e, h2e = S.random_packed_integrals(sorb, seed=8, symmetric=True)
+    lut = WavefunctionLUT(dev(keys), dev(psi), sorb, DEV, rank=0, world_size=1)
+    x = dev(keys[:48])
+    e1, _, p1 = local_energy_sample_space(x, dev(h1e), dev(h2e), lut, sorb, nele, noA, noB)
+    e3, _, p3 = local_energy_three_call(x, dev(h1e), dev(h2e), lut, sorb, nele, noA, noB, batch=16)
+    np.testing.assert_allclose(e1.cpu().numpy(), e3.cpu().numpy(), rtol=1e-12, atol=0)
+    assert torch.equal(p1, p3)
+    order = O.sort_onv(keys)
+    want = O.eloc_sample_space(keys[:6], h1e, h2e, keys[order], psi[order], sorb, nele, noA, noB)
+    np.testing.assert_allclose(e1[:6].cpu().numpy(), want, rtol=1e-12, atol=0)
+    # every one of the 1819 rows must have been found
+    comb, _ = ops.get_comb_tensor(x[:4], sorb, nele, noA, noB)
+    _, mask = ops.wavefunction_lut(lut.bra_key, comb.view(-1, 8), sorb, hash_index=lut.hash_index)
+    assert bool(mask.all())
+
+
+def test_eloc_multiword_onvs_against_oracle():
+    """L = 2 (100 spin orbitals) and L = 3 (132): one-pass E_loc vs the oracle on a small table."""
+    for sorb, noA, noB, nkeys in ((100, 3, 3, 4000), (132, 3, 2, 3000)):
+        # a table that contains real connections: a few seeds plus all their single/double excitations
+        seeds = S.random_onvs(3, sorb, noA, noB, seed=sorb)
+        comb = O.comb(seeds, sorb, noA, noB).reshape(-1, seeds.shape[1])
+        rng = np.random.default_rng(1)
+        pick = comb[rng.permutation(comb.shape[0])[: nkeys - 3]]
+        keys = np.unique(np.concatenate([seeds, pick]), axis=0)
+        psi = S.random_psi(keys.shape[0], seed=2, complex_=(sorb == 132))
+        h1e, h2e = S.random_packed_integrals(sorb, seed=3, symmetric=False)
+        lut = WavefunctionLUT(dev(keys), dev(psi), sorb, DEV, rank=0, world_size=1)
+        x = np.concatenate([seeds, keys[:5]])
+        dtype = torch.complex128 if sorb == 132 else torch.double
+        e1, _, _ = local_energy_sample_space(dev(x), dev(h1e), dev(h2e), lut, sorb, noA + noB, noA, noB, dtype)
+        order = O.sort_onv(keys)
+        want = O.eloc_sample_space(x, h1e, h2e, keys[order], psi[order], sorb, noA + noB, noA, noB)
+        np.testing.assert_allclose(e1.cpu().numpy(), want, rtol=1e-12, atol=0)
+
+
 # ---- larger, size-independent properties ---------------------------------------------------------------
 def test_fe2s2_shape_at_scale_properties():
     """Config-2 geometry (40 sorb, 15a15b, M = 7876) at 2e5 table keys / 8192 evaluated samples:
