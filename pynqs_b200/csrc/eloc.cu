@@ -396,33 +396,48 @@ eloc_eval_kernel(const u64 *__restrict__ bra, long long n, const double *__restr
 }
 
 // ---- host side --------------------------------------------------------------------------------------------
+constexpr long long kElocMaxCtas = 1 << 18;  // (samples x splits) per filter launch
+constexpr int kRowsPerSplit = 8192;         // a CTA filters at most this many rows (1024 per warp, queue of 256)
+
+// splits per sample: enough CTAs to fill the GPU when n is small, and never more than kRowsPerSplit
+// rows per CTA so that the per-warp candidate queues only overflow at hit rates above ~25 %
 int eloc_splits(long long n, int nsd) {
   if (n <= 0) return 1;
   long long want = (148LL * 8 + n - 1) / n;
-  long long cap = (nsd + 2047) / 2048;
-  if (cap < 1) cap = 1;
+  const long long cap = (nsd + 2047) / 2048 > 1 ? (nsd + 2047) / 2048 : 1;
   if (want > cap) want = cap;
+  const long long need = (nsd + kRowsPerSplit - 1) / kRowsPerSplit;
+  if (want < need) want = need;
   if (want < 1) want = 1;
   return (int)want;
 }
 
-constexpr long long kElocBatch = 1 << 18;   // samples per filter/eval launch pair
-constexpr long long kCandPerSample = 160;   // candidate buffer capacity per sample of a batch (+ slack)
+static long long eloc_batch(int nsd) {
+  const long long per_sample = (nsd + kRowsPerSplit - 1) / kRowsPerSplit > 1 ? (nsd + kRowsPerSplit - 1) / kRowsPerSplit : 1;
+  long long b = kElocMaxCtas / per_sample;
+  return b < 1024 ? 1024 : b;
+}
 
 struct ElocScratch {
   long long hii, runs, cursor, cand, total;
-  long long cand_cap;
+  long long cand_cap, batch;
+  int splits;  // same for every batch of the call (sized for the first, largest one)
 };
 
 static ElocScratch eloc_scratch_layout(long long n, int nsd) {
-  const long long nb = n < kElocBatch ? n : kElocBatch;
-  const int splits = eloc_splits(nb, nsd);
   ElocScratch l;
+  l.batch = eloc_batch(nsd);
+  const long long nb = n < l.batch ? n : l.batch;
+  const int splits = eloc_splits(nb, nsd);
+  l.splits = splits;
   l.hii = 0;
   l.runs = (l.hii + 8 * n + 15) / 16 * 16;
   l.cursor = l.runs + (long long)sizeof(CandRun) * nb * splits * kElocWarps;
   l.cand = l.cursor + 256;
-  l.cand_cap = nb * kCandPerSample + 65536;
+  // candidates per sample the global buffer can take before runs fall back to full evaluation:
+  // 160 (hits + overflowed buckets of a sparse table) or 1/32 of the rows, whichever is larger
+  const long long per_sample = nsd / 32 > 160 ? nsd / 32 : 160;
+  l.cand_cap = nb * per_sample + 65536;
   if (l.cand_cap > 0x7fffffffLL) l.cand_cap = 0x7fffffffLL;
   l.total = l.cand + 4 * l.cand_cap + 256;
   return l;
@@ -446,9 +461,9 @@ static int launch_eloc_LC(const u64 *bra, long long n, const double *h1e, const 
       cudaFuncSetAttribute(eloc_filter_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return check_launch("eloc_filter_kernel smem opt-in");
   const int w = CPLX ? 2 : 1;
-  for (long long b0 = 0; b0 < n; b0 += kElocBatch) {
-    const long long nb = n - b0 < kElocBatch ? n - b0 : kElocBatch;
-    const int splits = eloc_splits(nb, g.nsd);
+  for (long long b0 = 0; b0 < n; b0 += lay.batch) {
+    const long long nb = n - b0 < lay.batch ? n - b0 : lay.batch;
+    const int splits = lay.splits;
     if (cudaMemsetAsync(cursor, 0, 4, st) != cudaSuccess) return check_launch("eloc cursor memset");
     eloc_filter_kernel<L><<<(unsigned)(nb * splits), kElocThreads, smem, st>>>(bra + b0 * L, nb, iv, runs, cand, cursor,
                                                                                 (u32)lay.cand_cap, splits, g);

@@ -60,7 +60,8 @@ class WavefunctionLUT:
             idx = sort_onv(bra_key)
             self._bra_key = bra_key[idx].contiguous()
             self._wf_value = wf_value[idx].contiguous()
-            self.idx_sorted = torch.argsort(idx, stable=True)
+            self._sort_perm = idx
+            self._idx_sorted = None  # inverse permutation, built on first use (index_value only)
         else:
             self._bra_key = bra_key.contiguous()
             self._wf_value = wf_value.contiguous()
@@ -80,6 +81,15 @@ class WavefunctionLUT:
             from .C_extension import HashIndex
 
             self._hash = HashIndex(self._bra_key)
+
+    @property
+    def idx_sorted(self) -> Tensor:
+        """position of every input row in the sorted table (reference attribute, public_function.py:776)"""
+        if self._idx_sorted is None:
+            inv = torch.empty_like(self._sort_perm)
+            inv[self._sort_perm] = torch.arange(self._sort_perm.numel(), device=self._sort_perm.device)
+            self._idx_sorted = inv
+        return self._idx_sorted
 
     @property
     def bra_key(self) -> Tensor:

@@ -293,6 +293,22 @@ def test_eloc_multiword_onvs_against_oracle():
         np.testing.assert_allclose(e1.cpu().numpy(), want, rtol=1e-12, atol=0)
 
 
+def test_eloc_h50_shape_many_splits():
+    """Config-4 geometry: 100 spin orbitals, 25a25b, M = 571 876 (70 splits per sample, L = 2)."""
+    sorb, noA, noB = 100, 25, 25
+    seeds = S.random_onvs(2, sorb, noA, noB, seed=44)
+    comb = O.comb(seeds, sorb, noA, noB).reshape(-1, 16)
+    rng = np.random.default_rng(45)
+    keys = np.unique(np.concatenate([seeds, comb[rng.permutation(comb.shape[0])[:30000]]]), axis=0)
+    psi = S.random_psi(keys.shape[0], seed=46)
+    h1e, h2e = S.random_packed_integrals(sorb, seed=47, symmetric=False)
+    lut = WavefunctionLUT(dev(keys), dev(psi), sorb, DEV, rank=0, world_size=1)
+    e1, _, p1 = local_energy_sample_space(dev(seeds), dev(h1e), dev(h2e), lut, sorb, noA + noB, noA, noB)
+    order = O.sort_onv(keys)
+    want = O.eloc_sample_space(seeds, h1e, h2e, keys[order], psi[order], sorb, noA + noB, noA, noB)
+    np.testing.assert_allclose(e1.cpu().numpy(), want, rtol=1e-12, atol=0)
+
+
 # ---- larger, size-independent properties ---------------------------------------------------------------
 def test_fe2s2_shape_at_scale_properties():
     """Config-2 geometry (40 sorb, 15a15b, M = 7876) at 2e5 table keys / 8192 evaluated samples:
