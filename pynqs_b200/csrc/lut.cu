@@ -37,12 +37,18 @@ lut_indexed_kernel(const u64 *__restrict__ key, long long N, IndexView iv, const
   }
 }
 
-__global__ void index_header_kernel(HashHeader *hdr, u32 log2_dir, u64 N, u32 pool_buckets) {
-  hdr->log2_dir = log2_dir;
-  hdr->has_dup = 0;
-  hdr->n_keys = N;
-  hdr->cursor = 0;
-  hdr->pool_buckets = pool_buckets;
+// header + both directories: every slot {h = empty, off = 0, count = 0}
+__global__ void __launch_bounds__(256) index_init_kernel(HashHeader *hdr, uint4 *dir, u32 log2_dir, u64 N, u32 pool_buckets) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    hdr->log2_dir = log2_dir;
+    hdr->has_dup = 0;
+    hdr->n_keys = N;
+    hdr->cursor = 0;
+    hdr->pool_buckets = pool_buckets;
+  }
+  const size_t slots = (size_t)2 << log2_dir;
+  const uint4 empty = make_uint4(0xffffffffu, 0xffffffffu, 0u, 0u);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < slots; i += (size_t)gridDim.x * blockDim.x) dir[i] = empty;
 }
 
 __device__ __forceinline__ u32 dir_claim(DirSlot *dir, u32 log2_dir, u64 h) {
@@ -160,17 +166,11 @@ int launch_hash_build(const u64 *key, long long N, int L, void *ws, long long ws
   u32 *rows = reinterpret_cast<u32 *>(b + l.idx_off);
   u32 *slotB = reinterpret_cast<u32 *>(b + l.scratch_off);
   u32 *slotA = slotB + N;
-  // directories: h = all ones (empty); off / count = garbage-free after the second memset
-  if (cudaMemsetAsync(dirB, 0xff, (size_t)(l.pool_off - l.dir_off[0]), st) != cudaSuccess) return check_launch("index memset");
   if (cudaMemsetAsync(pool, 0, (size_t)(l.idx_off - l.pool_off), st) != cudaSuccess) return check_launch("index memset");
-  index_header_kernel<<<1, 1, 0, st>>>(hdr, l.log2_dir, (u64)N, (u32)l.pool_buckets);
+  index_init_kernel<<<148 * 8, 256, 0, st>>>(hdr, reinterpret_cast<uint4 *>(dirB), l.log2_dir, (u64)N, (u32)l.pool_buckets);
   count_launch();
   if (N > 0) {
     const unsigned blocks = (unsigned)((N + 255) / 256);
-    // the count field must start at zero: clear `off`/`lg` of every slot (h stays all ones)
-    // -- done by a strided 2-D memset over the 8 trailing bytes of each 16-byte slot
-    if (cudaMemset2DAsync(reinterpret_cast<char *>(dirB) + 8, sizeof(DirSlot), 0, 8, (size_t)2 << l.log2_dir, st) != cudaSuccess)
-      return check_launch("index memset2d");
     switch (L) {
       case 1: index_count_kernel<1><<<blocks, 256, 0, st>>>(key, N, hdr, dirB, dirA, slotB, slotA); break;
       case 2: index_count_kernel<2><<<blocks, 256, 0, st>>>(key, N, hdr, dirB, dirA, slotB, slotA); break;

@@ -58,8 +58,10 @@ def exchange_unique_samples(onv: Tensor, psi: Tensor, counts: Optional[Tensor] =
         gathered = torch.empty((world * n_max, rec_w), dtype=torch.uint8, device=dev)
         dist.all_gather_into_tensor(gathered, rec)
         gathered = gathered.view(world, n_max, rec_w)
-        parts = [gathered[r, : n_list[r]] for r in range(world)]
-        cat = torch.cat(parts)
+        if min(n_list) == n_max:  # equal pieces: the gathered buffer already is the concatenation
+            cat = gathered.view(world * n_max, rec_w)
+        else:
+            cat = torch.cat([gathered[r, : n_list[r]] for r in range(world)])
         all_onv = cat[:, :w].contiguous()
         pb = cat[:, w : w + pw].contiguous()
         all_psi = torch.view_as_complex(pb.view(torch.float64).view(-1, 2)) if cplx else pb.view(torch.float64).view(-1)
@@ -104,13 +106,24 @@ def energy_statistics(eloc: Tensor, prob: Tensor, counts: Optional[int] = None) 
     cplx = eloc.is_complex()
     e = eloc.to(torch.complex128) if cplx else eloc.to(torch.float64)
     p = prob.to(torch.float64)
-    w = p.sum()
-    mu = (e * p).sum() / w if e.numel() else torch.zeros((), dtype=e.dtype, device=e.device)
-    d = e - mu
-    m2 = ((d * d.conj()).real * p).sum() if cplx else (d * d * p).sum()
-    mu_re = mu.real if cplx else mu
-    mu_im = mu.imag if cplx else torch.zeros_like(mu_re)
-    vec = torch.stack([w, mu_re * 1.0, mu_im * 1.0, m2, torch.tensor(float(e.numel()), dtype=torch.float64, device=e.device)])
+    if e.numel():
+        # one pass: moments of d = E - c about the shift c = E[0] (stable: |d| is of the size of the
+        # spread), then M2 about the local mean mu = c + sum(p d) / w by the same exact identity
+        c = e[0]
+        d = e - c
+        if cplx:
+            rows = torch.stack([torch.ones_like(p), d.real, d.imag, d.real * d.real + d.imag * d.imag])
+        else:
+            rows = torch.stack([torch.ones_like(p), d, torch.zeros_like(p), d * d])
+        mom = rows @ p  # [w, sum p d_re, sum p d_im, sum p |d|^2]
+        w = mom[0]
+        dm_re, dm_im = mom[1] / w, mom[2] / w
+        m2 = mom[3] - w * (dm_re * dm_re + dm_im * dm_im)
+        mu_re = (c.real if cplx else c) + dm_re
+        mu_im = (c.imag + dm_im) if cplx else dm_im
+    else:
+        w = m2 = mu_re = mu_im = torch.zeros((), dtype=torch.float64, device=e.device)
+    vec = torch.stack([w, mu_re, mu_im, m2, torch.tensor(float(e.numel()), dtype=torch.float64, device=e.device)])
     if world > 1:
         allv = torch.empty(world * 5, dtype=torch.float64, device=vec.device)
         dist.all_gather_into_tensor(allv, vec)
