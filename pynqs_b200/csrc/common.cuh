@@ -195,9 +195,12 @@ __device__ __forceinline__ void build_lists(const Onv<L> &x, int sorb, int noA, 
 // triangular pair index t -> (hi, lo), hi > lo >= 0.  The reference computes
 // hi = int(sqrt(2(t+1)) + 0.5) in FP64 (excitation.h:6-11); 2(t+1) lies in
 // [hi^2-hi+2, hi^2+hi], strictly inside ((hi-.5)^2, (hi+.5)^2), so any correctly rounded
-// single-precision sqrt followed by round-to-nearest yields the same integer for hi < 2^11.
+// single-precision sqrt (even the approximate MUFU one) followed by round-to-nearest yields the same
+// integer for hi < 2^11.
 __device__ __forceinline__ void tri_unpack(int t, int &hi, int &lo) {
-  hi = __float2int_rn(sqrtf((float)(2 * t + 2)));
+  float r;
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"((float)(2 * t + 2)));  // error ~1e-6 relative, margin ~1e-2
+  hi = __float2int_rn(r);
   lo = t - ((hi * (hi - 1)) >> 1);
 }
 

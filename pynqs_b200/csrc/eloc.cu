@@ -174,7 +174,7 @@ __device__ __forceinline__ void eloc_filter_chunk(const Onv<L> &x, const u64 *au
   bool any = false;
 #pragma unroll
   for (int j = 0; j < ROWS; ++j) {
-    cand[j] = tag[j] && (tags_match(t[j], tag[j]) || bucket_overflowed(t[j]));
+    cand[j] = tag[j] && probe_residue(t[j], tag[j]) == 0u;
     any |= cand[j];
   }
   if (__any_sync(0xffffffffu, any)) {
@@ -201,8 +201,171 @@ __device__ __forceinline__ void eloc_filter_class(const Onv<L> &x, const u64 *au
   }
 }
 
+// Same-spin doubles (BETA = false: alpha-alpha rows [d1, d2), own beta region; true: beta-beta rows
+// [d2, d3), own alpha region).  Row r = base + ab * nH + k uses particle pair ab and hole pair
+// ij = r % nH = (k + base) % nH (the reference takes the GLOBAL index modulo nH, quirk Q1), i.e. the
+// hole pairs of one particle pair are cyclically shifted by base % nH.  Work unit = (particle pair,
+// block of 32 hole pairs): lane l owns hole pair ij = 32 blk + l, so there is no division per row;
+// the particle-pair mask is warp-uniform.  Two units are in flight per iteration.
+template <int L, bool BETA>
+__device__ __forceinline__ void eloc_filter_ss(const Onv<L> &x, const u64 *msk, const TableOffsets &to, const ExcGeom &g, u64 own,
+                                               const TagBucket *__restrict__ pool, u32 *queue, u32 &qn, int lo, int hi) {
+  if (lo >= hi || own == kNoRegion) return;
+  constexpr int U = 2;
+  const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const u32 nH = (u32)(BETA ? g.noBB : g.noAA), nP = (u32)(BETA ? g.nvBB : g.nvAA);
+  const u32 base = (u32)(BETA ? g.d2 : g.d1);
+  const u64 *hp = msk + (BETA ? to.hpb : to.hpa), *pp = msk + (BETA ? to.ppb : to.ppa);
+  const u32 shift = base - fdiv(base, BETA ? g.by_noBB : g.by_noAA) * nH;  // base % nH
+  const u32 nblk = (nH + 31u) >> 5;
+  const u32 roff = (u32)own, sh32 = (u32)(own >> 32);
+  // unit u = ab * nblk + blk; this warp takes units warp, warp + 8, ... -- (ab, blk) advanced incrementally
+  const u32 step_ab = (u32)kElocWarps / nblk, step_blk = (u32)kElocWarps - step_ab * nblk;
+  u32 ab = warp / nblk, blk = warp - ab * nblk;
+  while (ab < nP) {
+    uint4 t[U];
+    u32 tag[U], row[U];
+#pragma unroll
+    for (int i = 0; i < U; ++i) {
+      tag[i] = 0;
+      row[i] = 0;
+      const u32 ij = (blk << 5) + lane;
+      if (ab < nP && ij < nH) {
+        const u32 k = ij >= shift ? ij - shift : ij + nH - shift;
+        const u32 r = base + ab * nH + k;
+        if (r >= (u32)lo && r < (u32)hi) {
+          const Onv<L> y = msk_apply<L>(msk_apply<L>(x, hp[ij]), pp[ab]);
+          const u64 h2 = BETA ? hash_beta<L>(y) : hash_alpha<L>(y);
+          row[i] = r;
+          tag[i] = hash_tag(h2);
+          const u32 bucket = roff + shr_clamp((u32)(h2 >> 32), sh32);
+          t[i] = __ldg(pool + bucket);
+        }
+      }
+      ab += step_ab;
+      blk += step_blk;
+      if (blk >= nblk) {
+        blk -= nblk;
+        ++ab;
+      }
+    }
+    u32 res[U];
+    bool any = false;
+#pragma unroll
+    for (int i = 0; i < U; ++i) {
+      res[i] = tag[i] ? probe_residue(t[i], tag[i]) : 1u;
+      any |= res[i] == 0u;
+    }
+    if (__any_sync(0xffffffffu, any)) {
+      const u32 lt = (1u << lane) - 1u;
+#pragma unroll
+      for (int i = 0; i < U; ++i) {
+        const u32 m = __ballot_sync(0xffffffffu, res[i] == 0u);
+        const u32 slot = qn + __popc(m & lt);
+        if (res[i] == 0u && slot < (u32)kCandPerWarp) queue[slot] = row[i];
+        qn += __popc(m);
+      }
+    }
+  }
+}
+
+// Alpha-beta doubles, whole runs: rows r = d3 + jb * sA + ia for jb in [jb_begin, jb_end), all ia.
+// The warp walks the beta excitations jb assigned to it.  The region of the excited beta string is
+// warp-uniform (one broadcast shared load; when no key has that string the whole run of sA rows is
+// skipped), and lane l always handles the alpha excitations ia = l + 32 j, so the hashes of ITS
+// excited alpha strings stay in registers for the whole sample: a row costs a shift, a 64-bit
+// multiply-add for the address and the 16-byte gather of its four tags, then a branch-free test
+// (probe_residue) -- no division, no per-row shared-memory traffic.  Two runs are in flight.
+// Requires sA <= 32 * RA (RA <= 4); larger alpha tables use the generic row loop.
+template <int L, int RA>
+__device__ __forceinline__ void eloc_filter_ab_runs(const u64 *aux_sa, const u64 *aux_sb, const ExcGeom &g,
+                                                    const TagBucket *__restrict__ pool, u32 *queue, u32 &qn, u32 jb_begin, u32 jb_end) {
+  constexpr int JB = 2;
+  const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const u32 sA = (u32)g.sA;
+  u32 tag[RA], hhi[RA];
+#pragma unroll
+  for (int j = 0; j < RA; ++j) {
+    // slots beyond sA repeat the last valid one: harmless duplicate probes, masked out when queued
+    const u32 ia = min(lane + 32u * j, sA - 1u);
+    const uint2 h = *reinterpret_cast<const uint2 *>(aux_sa + ia);
+    tag[j] = h.x | 3u;
+    hhi[j] = h.y;
+  }
+  for (u32 jb0 = jb_begin + warp; jb0 < jb_end; jb0 += JB * kElocWarps) {
+    uint4 t[JB][RA];
+    bool live[JB];
+#pragma unroll
+    for (int b = 0; b < JB; ++b) {
+      const u32 jb = jb0 + b * kElocWarps;
+      uint2 d = make_uint2(0u, ~0u);
+      if (jb < jb_end) d = *reinterpret_cast<const uint2 *>(aux_sb + jb);  // (first bucket, 32 - log2 buckets), warp-uniform
+      live[b] = d.y != ~0u;
+      if (live[b]) {
+#pragma unroll
+        for (int j = 0; j < RA; ++j) {
+          const u32 bucket = d.x + shr_clamp(hhi[j], d.y);  // 32-bit index arithmetic, one 64-bit address per load
+          t[b][j] = __ldg(pool + bucket);
+        }
+      }
+    }
+#pragma unroll
+    for (int b = 0; b < JB; ++b) {
+      if (!live[b]) continue;  // warp-uniform
+      u32 res[RA];
+      u32 worst = 1u;
+#pragma unroll
+      for (int j = 0; j < RA; ++j) {
+        res[j] = probe_residue(t[b][j], tag[j]);
+        worst = min(worst, res[j]);
+      }
+      if (__any_sync(0xffffffffu, worst == 0u)) {
+        const u32 lt = (1u << lane) - 1u;
+        const u32 jb = jb0 + b * kElocWarps;
+#pragma unroll
+        for (int j = 0; j < RA; ++j) {
+          const bool c = res[j] == 0u && lane + 32u * j < sA;
+          const u32 m = __ballot_sync(0xffffffffu, c);
+          const u32 slot = qn + __popc(m & lt);
+          if (c && slot < (u32)kCandPerWarp) queue[slot] = (u32)g.d3 + jb * sA + lane + 32 * j;
+          qn += __popc(m);  // may exceed the capacity: recorded as overflow at the end
+        }
+      }
+    }
+  }
+}
+
+// alpha-beta class of a split [lo, hi): whole runs through the register-resident fast path, the
+// partial runs at the split boundaries (and alpha tables beyond 128 entries) through the row loop
 template <int L>
-__global__ void __launch_bounds__(kElocThreads)
+__device__ __forceinline__ void eloc_filter_ab(const Onv<L> &x, const u64 *aux, const u64 *msk, const TableOffsets &to,
+                                               const ExcGeom &g, const TagBucket *__restrict__ pool, u32 *queue, u32 &qn, int lo,
+                                               int hi) {
+  if (lo >= hi) return;
+  const u32 sA = (u32)g.sA;
+  if (sA > 128u) {
+    eloc_filter_class<L, 4, kElocRows>(x, aux, msk, to, g, kNoRegion, pool, queue, qn, lo, hi);
+    return;
+  }
+  const u32 q_lo = (u32)(lo - g.d3), q_hi = (u32)(hi - g.d3);
+  const u32 jb_begin = fdiv(q_lo + sA - 1u, g.by_sA), jb_end = fdiv(q_hi, g.by_sA);  // whole runs [jb_begin, jb_end)
+  if (jb_begin >= jb_end) {  // the split holds no whole run
+    eloc_filter_class<L, 4, kElocRows>(x, aux, msk, to, g, kNoRegion, pool, queue, qn, lo, hi);
+    return;
+  }
+  const int head_hi = g.d3 + (int)(jb_begin * sA);
+  if (lo < head_hi) eloc_filter_class<L, 4, kElocRows>(x, aux, msk, to, g, kNoRegion, pool, queue, qn, lo, head_hi);
+  const u64 *aux_sa = aux + to.sa, *aux_sb = aux + to.sb;
+  if (sA <= 32u) eloc_filter_ab_runs<L, 1>(aux_sa, aux_sb, g, pool, queue, qn, jb_begin, jb_end);
+  else if (sA <= 64u) eloc_filter_ab_runs<L, 2>(aux_sa, aux_sb, g, pool, queue, qn, jb_begin, jb_end);
+  else if (sA <= 96u) eloc_filter_ab_runs<L, 3>(aux_sa, aux_sb, g, pool, queue, qn, jb_begin, jb_end);
+  else eloc_filter_ab_runs<L, 4>(aux_sa, aux_sb, g, pool, queue, qn, jb_begin, jb_end);
+  const int tail_lo = g.d3 + (int)(jb_end * sA);
+  if (tail_lo < hi) eloc_filter_class<L, 4, kElocRows>(x, aux, msk, to, g, kNoRegion, pool, queue, qn, tail_lo, hi);
+}
+
+template <int L>
+__global__ void __launch_bounds__(kElocThreads, 4)
 eloc_filter_kernel(const u64 *__restrict__ bra, long long n, IndexView iv, CandRun *__restrict__ runs, u32 *__restrict__ cand,
                    u32 *cursor, u32 cand_cap, int splits, ExcGeom g) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -213,8 +376,8 @@ eloc_filter_kernel(const u64 *__restrict__ bra, long long n, IndexView iv, CandR
   u32 *queues = reinterpret_cast<u32 *>(msk + to.total);
   __shared__ u64 s_own[2];  // probe descriptors of the regions of the sample's own beta / alpha string
 
-  const long long s = blockIdx.x / splits;
-  const int split = blockIdx.x - (int)(s * splits);
+  const long long s = splits == 1 ? (long long)blockIdx.x : (long long)(blockIdx.x / (unsigned)splits);
+  const int split = splits == 1 ? 0 : (int)(blockIdx.x - (unsigned)s * (unsigned)splits);
   if (s >= n) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   CandRun *my_run = runs + (s * splits + split) * kElocWarps + warp;
@@ -241,7 +404,7 @@ eloc_filter_kernel(const u64 *__restrict__ bra, long long n, IndexView iv, CandR
   });
   __syncthreads();
 
-  const int chunk = (g.nsd + splits - 1) / splits;
+  const int chunk = splits == 1 ? g.nsd : (int)(((unsigned)g.nsd + (unsigned)splits - 1u) / (unsigned)splits);
   const int r_begin = split * chunk;
   const int r_end = min(g.nsd, r_begin + chunk);
   u32 *queue = queues + warp * kCandPerWarp;
@@ -249,9 +412,9 @@ eloc_filter_kernel(const u64 *__restrict__ bra, long long n, IndexView iv, CandR
   const u64 own_b = s_own[0], own_a = s_own[1];
   auto lo = [&](int v) { return v > r_begin ? v : r_begin; };
   auto hi = [&](int v) { return v < r_end ? v : r_end; };
-  eloc_filter_class<L, 4, kElocRows>(x, aux, msk, to, g, own_b, iv.pool, queue, qn, lo(g.d3), hi(g.nsd));
-  eloc_filter_class<L, 2, kElocRows>(x, aux, msk, to, g, own_b, iv.pool, queue, qn, lo(g.d1), hi(g.d2));
-  eloc_filter_class<L, 3, kElocRows>(x, aux, msk, to, g, own_a, iv.pool, queue, qn, lo(g.d2), hi(g.d3));
+  eloc_filter_ab<L>(x, aux, msk, to, g, iv.pool, queue, qn, lo(g.d3), hi(g.nsd));
+  eloc_filter_ss<L, false>(x, msk, to, g, own_b, iv.pool, queue, qn, lo(g.d1), hi(g.d2));
+  eloc_filter_ss<L, true>(x, msk, to, g, own_a, iv.pool, queue, qn, lo(g.d2), hi(g.d3));
   eloc_filter_class<L, 0, 1>(x, aux, msk, to, g, own_b, iv.pool, queue, qn, lo(0), hi(g.d0));
   eloc_filter_class<L, 1, 1>(x, aux, msk, to, g, own_a, iv.pool, queue, qn, lo(g.d0), hi(g.d1));
 

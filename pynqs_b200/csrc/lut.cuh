@@ -91,17 +91,29 @@ __host__ __device__ inline IndexView index_view(const void *ws, long long N) {
   return v;
 }
 
-// 64-bit hash of one spin string: the words of the ONV masked to the even (which = 1, alpha) or
-// odd (which = 0, beta) bits.  Never returns kDirEmpty.
+// 64-bit hash of one spin string: the words of the ONV masked to the even (alpha) or odd (beta)
+// bits.  Two independent 32-bit multiply-xorshift mixes of the word halves (32-bit integer ops only:
+// a 64-bit multiply costs ~4 of them on the GPU): the LOW word feeds the bucket tags, the HIGH word
+// the directory slot and the bucket index inside a region.  Never returns kDirEmpty.
 template <int L>
 __device__ __forceinline__ u64 hash_string(const Onv<L> &x, u64 spin_mask) {
-  u64 h = (x.w[0] & spin_mask) * 0x9E3779B97F4A7C15ull;
+  u32 a = (u32)(x.w[0] & spin_mask), b = (u32)((x.w[0] & spin_mask) >> 32);
 #pragma unroll
-  for (int i = 1; i < L; ++i) h = (h ^ (h >> 29) ^ (x.w[i] & spin_mask)) * 0xBF58476D1CE4E5B9ull;
-  h ^= h >> 32;
-  h *= 0xD6E8FEB86659FD93ull;
-  h ^= h >> 29;
-  return h == kDirEmpty ? kDirEmpty - 1 : h;
+  for (int i = 1; i < L; ++i) {
+    const u64 w = x.w[i] & spin_mask;
+    a = (a ^ (a >> 15)) * 0x2C1B3C6Du + (u32)w;
+    b = (b ^ (b >> 13)) * 0x297A2D39u + (u32)(w >> 32);
+  }
+  u32 lo = a * 0x9E3779B1u ^ b * 0x85EBCA77u;
+  u32 hi = a * 0x27D4EB2Fu + b * 0x165667B1u;
+  lo ^= lo >> 15;
+  lo *= 0xC2B2AE3Du;
+  lo ^= lo >> 13;
+  hi ^= hi >> 16;
+  hi *= 0x7FEB352Du;
+  hi ^= hi >> 15;
+  if (hi == 0xffffffffu) hi = 0xfffffffeu;
+  return ((u64)hi << 32) | lo;
 }
 template <int L>
 __device__ __forceinline__ u64 hash_alpha(const Onv<L> &x) { return hash_string<L>(x, kEven); }
@@ -113,6 +125,12 @@ __device__ __forceinline__ bool tags_match(const uint4 &t, u32 tag) {
   return t.x == tag || t.y == tag || t.z == tag || (t.w | 1u) == tag;
 }
 __device__ __forceinline__ bool bucket_overflowed(const uint4 &t) { return t.w != 0u && !(t.w & 1u); }
+// branch-free "this probe cannot be rejected": 0 iff a tag matches or the bucket has overflowed.
+// (stored tags end in binary 11; an overflowed bucket's last tag ends in 10; empty slots are 0)
+__device__ __forceinline__ u32 probe_residue(const uint4 &t, u32 tag) {
+  const u32 a = min(t.x ^ tag, t.y ^ tag), b = min(t.z ^ tag, (t.w | 1u) ^ tag);
+  return min(min(a, b), (t.w & 3u) ^ 2u);
+}
 
 // region descriptor packed in 64 bits: off | lg << 32; kNoRegion when the group does not exist
 constexpr u64 kNoRegion = ~0ull;

@@ -27,14 +27,16 @@ def _world() -> Tuple[int, int]:
     return 0, 1
 
 
-def exchange_unique_samples(onv: Tensor, psi: Tensor, counts: Optional[Tensor] = None, disjoint: bool = False
-                            ) -> Tuple[Tensor, Tensor, Tensor]:
+def exchange_unique_samples(onv: Tensor, psi: Tensor, counts: Optional[Tensor] = None, disjoint: bool = False,
+                            equal_sizes: bool = False) -> Tuple[Tensor, Tensor, Tensor]:
     """All ranks contribute their locally unique ONVs (uint8 [n_r, 8L]), psi values and sample
     counts; every rank returns the same merged (unique_onv, psi, counts).
 
     Merge order = the reference's (sample.py:672-698): if `disjoint` (use_same_tree) plain
     concatenation in rank order, else torch.unique(dim=0) order (row-lexicographic, byte 0 most
-    significant) with psi taken from the first occurrence and counts summed."""
+    significant) with psi taken from the first occurrence and counts summed.
+    `equal_sizes`: the caller guarantees every rank contributes the same number of rows, which saves
+    the all-gather of the counts and its host synchronisation."""
     rank, world = _world()
     dev = onv.device
     n_r, w = onv.shape
@@ -47,9 +49,12 @@ def exchange_unique_samples(onv: Tensor, psi: Tensor, counts: Optional[Tensor] =
     if world == 1:
         all_onv, all_psi, all_cnt = onv, psi, counts
     else:
-        n_all = torch.empty(world, dtype=torch.int64, device=dev)
-        dist.all_gather_into_tensor(n_all, torch.tensor([n_r], dtype=torch.int64, device=dev))
-        n_list = n_all.tolist()
+        if equal_sizes:
+            n_list = [n_r] * world
+        else:
+            n_all = torch.empty(world, dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(n_all, torch.tensor([n_r], dtype=torch.int64, device=dev))
+            n_list = n_all.tolist()
         n_max = max(n_list)
         rec = torch.zeros((n_max, rec_w), dtype=torch.uint8, device=dev)
         rec[:n_r, :w] = onv
