@@ -230,7 +230,7 @@ def run_ours(args):
 
     from pynqs_b200 import _lib
     from pynqs_b200 import C_extension as ops
-    from pynqs_b200.distributed import energy_statistics, exchange_unique_samples, rank_slice
+    from pynqs_b200.distributed import energy_statistics_amplitudes, exchange_unique_samples, rank_slice
     from pynqs_b200.lut import WavefunctionLUT, split_length_idx
 
     _lib.load()
@@ -247,29 +247,36 @@ def run_ours(args):
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
     host_eloc = torch.empty(hi - lo + 1, dtype=torch.float64).pin_memory()
 
-    kern_ms = []
+    kern_ms, phase_ev = [], []
     equal_sizes = n_total % world == 0
 
     def step(from_host: bool):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+        ev[0].record()
         if from_host:
             k = host_keys.to(dev, non_blocking=True)
             p = host_psi.to(dev, non_blocking=True)
         else:
             k, p = d_keys, d_psi
         uniq, wf, cnt = exchange_unique_samples(k, p, None, disjoint=True, equal_sizes=equal_sizes)
+        ev[1].record()
         lut = WavefunctionLUT(uniq, wf, SORB, dev, sort=not args.unsorted_table, rank=rank, world_size=world)
         b, e = rank_slice(uniq.size(0), rank, world)
         x = uniq[b:e]
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0, e1 = ev[2], ev[3]
         e0.record()
         eloc, psi0 = ops.eloc_sample_space(x, h1e, h2e, SORB, NELE, NOA, NOB, lut.bra_key, lut.wf_value, lut.hash_index)
         e1.record()
-        prob = psi0 * psi0 / (lut.wf_value * lut.wf_value).sum() * world  # reference convention: prob * world_size
-        st = energy_statistics(eloc, prob)
+        # p_i = |psi_i|^2 / sum_table |psi|^2 * world (reference convention, sample.py:772); the ranks' slices
+        # partition the table, so the norm comes out of the statistics' own all-gather
+        st = energy_statistics_amplitudes(eloc, psi0)
         if from_host:
             host_eloc[: e - b].copy_(eloc, non_blocking=True)
             torch.cuda.current_stream().synchronize()
+        ev[4].record()
         kern_ms.append((e0, e1, e - b))
+        if not from_host:
+            phase_ev.append(ev)
         return st
 
     def timed(n_steps: int, from_host: bool):
@@ -294,6 +301,7 @@ def run_ours(args):
         step(False)
     torch.cuda.synchronize()
     kern_ms.clear()
+    phase_ev.clear()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -302,6 +310,8 @@ def run_ours(args):
     launches = _lib.launch_count() - l0
     kern = [(a.elapsed_time(b), n) for a, b, n in kern_ms]
     e2e_ms, st2 = timed(args.steps, True)
+    names = ["exchange", "table_sort_and_index", "eloc_kernels", "probabilities_and_statistics"]
+    phases = {nm: sum(ev[i].elapsed_time(ev[i + 1]) for ev in phase_ev) / len(phase_ev) for i, nm in enumerate(names)}
     clocks = sampler.stop() if rank == 0 else None
 
     ms_per_step = total_ms / args.steps
@@ -338,6 +348,7 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n_total * 16), "d2h_bytes_per_step": int(n_total * 8 + 40 * world),
                 "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": int(launches),
+        "phases_ms_rank0": phases,
         "clocks": clocks,
         "energy": {"mean": st["mean"], "var": st["var"], "mean_e2e": st2["mean"]},
     }

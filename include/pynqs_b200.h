@@ -119,6 +119,25 @@ int pynqs_eloc_sample_space(const uint8_t *bra, int64_t n, const double *h1e, co
                             int64_t N, const void *hash_ws, void *scratch, int64_t scratch_bytes, void *eloc,
                             void *psi0, void *stream);
 
+/* ---- unique-sample table: sort (utils/public_function.py:626-689, 754-788) ----------------------
+ * Stable ascending sort of N keys (uint64[N, L] little-endian multi-word integers, the order of the
+ * reference's torch_sort_onv) together with their psi values (psi_bytes = 8 or 16 per row; psi may
+ * be NULL).  key_out / psi_out receive the sorted table, perm_out (int64[N], may be NULL) the source
+ * row of every sorted row.  sorb > 0 promises that bits >= sorb of every key are zero (then only the
+ * significant bits are sorted); sorb <= 0 sorts on all 64 L bits.  ws: pynqs_sort_bytes(N) bytes. */
+int64_t pynqs_sort_bytes(int64_t N);
+int pynqs_sort_table(const uint8_t *key, const void *psi, int64_t N, int L, int sorb, int psi_bytes, uint8_t *key_out,
+                     void *psi_out, int64_t *perm_out, void *ws, int64_t ws_bytes, void *stream);
+
+/* ---- energy statistics (utils/stats/dist_stats.py:18-79) -----------------------------------------
+ * out[7] = { sum w, sum w Re d, sum w Im d, sum w |d|^2, Re c, Im c, n } with d = eloc - c, c = eloc[0];
+ * eloc: double[n] or interleaved complex128[n] (eloc_complex).  weight_kind 0: w = weight (double[n]);
+ * 1: w = weight^2 (real amplitudes, double[n]); 2: w = |weight|^2 (complex128[n]).  Deterministic.
+ * scratch: pynqs_moments_scratch_bytes() bytes, ZEROED once by the caller before its first use. */
+int64_t pynqs_moments_scratch_bytes(void);
+int pynqs_weighted_moments(const void *eloc, int eloc_complex, const void *weight, int weight_kind, int64_t n, void *scratch,
+                           double *out, void *stream);
+
 /* number of kernel launches issued by this library in this process (bench.py's gpu_launches). */
 int64_t pynqs_launch_count(void);
 

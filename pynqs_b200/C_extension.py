@@ -389,6 +389,80 @@ def eloc_sample_space(
     return eloc, psi0
 
 
+# ---- the steps either side of the kernels: table sort and energy moments ------------------------
+def sort_table(bra_key: Tensor, wf_value: Tensor | None = None, sorb: int = 0, want_perm: bool = True):
+    """Stable ascending sort of ONV rows as little-endian multi-word integers -- the order of the
+    reference's torch_sort_onv (utils/public_function.py:626-689) -- applied to the keys and their
+    values in one go.  Returns (sorted keys, sorted values or None, source row of every sorted row
+    or None).  sorb > 0 promises that no key has a bit >= sorb set."""
+    dev = _need_cuda(bra_key) if wf_value is None else _need_cuda(bra_key, wf_value)
+    _contig(bra_key, "bra_key")
+    L = _onv_words(bra_key, "bra_key")
+    if bra_key.dim() != 2:
+        raise ValueError("bra_key must be 2-D")
+    N = bra_key.size(0)
+    psi_bytes = 0
+    if wf_value is not None:
+        _contig(wf_value, "wf_value")
+        if wf_value.dim() != 1 or wf_value.numel() != N or wf_value.element_size() not in (8, 16):
+            raise ValueError("wf_value must hold one 8- or 16-byte value per key")
+        psi_bytes = wf_value.element_size()
+    key_out = torch.empty_like(bra_key)
+    psi_out = torch.empty_like(wf_value) if wf_value is not None else None
+    perm = torch.empty(N, dtype=torch.int64, device=dev) if want_perm else None
+    if N == 0:
+        return key_out, psi_out, perm
+    lib = _lib.load()
+    nbytes = int(lib.pynqs_sort_bytes(i64(N)))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(
+            lib.pynqs_sort_table(
+                vp(bra_key.data_ptr()), vp(wf_value.data_ptr() if wf_value is not None else None), i64(N), L, int(sorb), psi_bytes or 8,
+                vp(key_out.data_ptr()), vp(psi_out.data_ptr() if psi_out is not None else None),
+                vp(perm.data_ptr() if perm is not None else None), vp(ws.data_ptr()), i64(nbytes), _stream(dev),
+            )
+        )
+    return key_out, psi_out, perm
+
+
+_moment_scratch: dict = {}
+
+
+def weighted_moments(eloc: Tensor, weight: Tensor, weight_is_amplitude: bool = False) -> Tensor:
+    """[sum w, sum w Re d, sum w Im d, sum w |d|^2, Re c, Im c, n] (float64[7] on the device) with
+    d = eloc - c, c = eloc[0]; w = weight, or |weight|^2 when weight_is_amplitude.  One kernel,
+    deterministic; the building block of utils/stats/dist_stats.py:18-79."""
+    dev = _need_cuda(eloc, weight)
+    _contig(eloc, "eloc")
+    _contig(weight, "weight")
+    if eloc.dtype not in (torch.float64, torch.complex128) or eloc.dim() != 1 or weight.shape != eloc.shape:
+        raise ValueError("eloc must be 1-D float64/complex128 and weight of the same shape")
+    if weight_is_amplitude:
+        if weight.dtype not in (torch.float64, torch.complex128):
+            raise ValueError("amplitudes must be float64/complex128")
+        kind = 2 if weight.dtype == torch.complex128 else 1
+    else:
+        if weight.dtype != torch.float64:
+            raise ValueError("weights must be float64")
+        kind = 0
+    lib = _lib.load()
+    key = (dev.index, torch.cuda.current_stream(dev).cuda_stream)
+    scratch = _moment_scratch.get(key)
+    if scratch is None:
+        scratch = torch.zeros(int(lib.pynqs_moments_scratch_bytes()), dtype=torch.uint8, device=dev)
+        _moment_scratch[key] = scratch
+    out = torch.empty(7, dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(
+            lib.pynqs_weighted_moments(
+                vp(eloc.data_ptr()), int(eloc.is_complex()), vp(weight.data_ptr()), kind, i64(eloc.numel()), vp(scratch.data_ptr()),
+                vp(out.data_ptr()), _stream(dev),
+            )
+        )
+    return out
+
+
 # ---- names outside the hot path that callers import (SURVEY.md section 8b) -----------------------
 def merge_rank_sample(idx: Tensor, counts: Tensor, split_idx: Tensor, length: int) -> Tensor:
     """merge_counts[idx[i]] += counts[i] (C_extension.pyi:256-279); torch index_add_ (atomic, unlike

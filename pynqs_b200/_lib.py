@@ -14,7 +14,9 @@ SYMBOLS = [
     "pynqs_tensor_to_onv", "pynqs_onv_to_tensor", "pynqs_comb", "pynqs_prepared_bytes", "pynqs_prepare_integrals",
     "pynqs_comb_hij_fused", "pynqs_hij",
     "pynqs_lut", "pynqs_hash_bytes", "pynqs_hash_build", "pynqs_lut_hashed",
-    "pynqs_eloc_scratch_bytes", "pynqs_eloc_sample_space", "pynqs_launch_count",
+    "pynqs_eloc_scratch_bytes", "pynqs_eloc_sample_space",
+    "pynqs_sort_bytes", "pynqs_sort_table", "pynqs_moments_scratch_bytes", "pynqs_weighted_moments",
+    "pynqs_launch_count",
 ]
 
 OK, EVALUE, EOVERFLOW, ECUDA, EWORKSPACE = 0, 1, 2, 3, 4
@@ -41,6 +43,8 @@ def load() -> ctypes.CDLL:
         getattr(lib, s)  # raises AttributeError if the build is stale
     lib.pynqs_last_error.restype = ctypes.c_char_p
     lib.pynqs_launch_count.restype = ctypes.c_int64
+    lib.pynqs_sort_bytes.restype = ctypes.c_int64
+    lib.pynqs_moments_scratch_bytes.restype = ctypes.c_int64
     if lib.pynqs_abi_version() != 1:
         raise RuntimeError("libpynqs_b200.so ABI version mismatch")
     _lib = lib

@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libpynqs_b200.so")
-SOURCES = ["abi.cu", "enumerate.cu", "hij.cu", "lut.cu", "eloc.cu", "convert.cu", "prepare.cu"]
+SOURCES = ["abi.cu", "enumerate.cu", "hij.cu", "lut.cu", "eloc.cu", "convert.cu", "prepare.cu", "table.cu"]
 HEADERS = ["common.cuh", "lut.cuh", "tables.cuh", "prepare.cuh", os.path.join("..", "..", "include", "pynqs_b200.h")]
 
 NVCC_FLAGS = [

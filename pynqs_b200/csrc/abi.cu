@@ -49,6 +49,10 @@ int launch_lut_hashed(const u64 *, long long, const u64 *, long long, int, const
 long long eloc_scratch_bytes(long long, int, int);
 int launch_eloc(const u64 *, long long, const double *, const double *, const u64 *, const double *, int, long long,
                 const void *, void *, long long, double *, double *, const ExcGeom &, cudaStream_t);
+long long sort_workspace_bytes(long long);
+int launch_sort_table(const u64 *, const void *, long long, int, int, int, u64 *, void *, long long *, void *, long long, cudaStream_t);
+long long moments_scratch_bytes();
+int launch_moments(const double *, int, const double *, int, long long, void *, double *, cudaStream_t);
 int launch_onv_to_tensor(const u64 *, void *, int, long long, int, cudaStream_t);
 int launch_tensor_to_onv(const unsigned char *, unsigned char *, long long, int, cudaStream_t);
 
@@ -254,6 +258,29 @@ int pynqs_eloc_sample_space(const uint8_t *bra, int64_t n, const double *h1e, co
   return launch_eloc(reinterpret_cast<const u64 *>(bra), n, h1e, h2e, reinterpret_cast<const u64 *>(key),
                      (const double *)psi, psi_complex, N, hash_ws, scratch, scratch_bytes, (double *)eloc, (double *)psi0, g,
                      (cudaStream_t)stream);
+}
+
+int64_t pynqs_sort_bytes(int64_t N) { return sort_workspace_bytes(N < 0 ? 0 : N); }
+
+int pynqs_sort_table(const uint8_t *key, const void *psi, int64_t N, int L, int sorb, int psi_bytes, uint8_t *key_out,
+                     void *psi_out, int64_t *perm_out, void *ws, int64_t ws_bytes, void *stream) {
+  if (N < 0 || L < 1 || L > PYNQS_MAX_SORB_LEN || (psi != nullptr && psi_bytes != 8 && psi_bytes != 16) || sorb > 64 * L) {
+    set_error("sort_table: bad N = %lld, L = %d, sorb = %d or psi_bytes = %d", (long long)N, L, sorb, psi_bytes);
+    return PYNQS_EVALUE;
+  }
+  return launch_sort_table(reinterpret_cast<const u64 *>(key), psi, N, L, sorb, psi_bytes, reinterpret_cast<u64 *>(key_out), psi_out,
+                           reinterpret_cast<long long *>(perm_out), ws, ws_bytes, (cudaStream_t)stream);
+}
+
+int64_t pynqs_moments_scratch_bytes(void) { return moments_scratch_bytes(); }
+
+int pynqs_weighted_moments(const void *eloc, int eloc_complex, const void *weight, int weight_kind, int64_t n, void *scratch,
+                           double *out, void *stream) {
+  if (n < 0 || weight_kind < 0 || weight_kind > 2) {
+    set_error("weighted_moments: bad n = %lld or weight_kind = %d", (long long)n, weight_kind);
+    return PYNQS_EVALUE;
+  }
+  return launch_moments((const double *)eloc, eloc_complex, (const double *)weight, weight_kind, n, scratch, out, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -4,7 +4,8 @@
 // Build, all asynchronous on the caller's stream (no host round trip, no sort):
 //   1. count : every key claims / finds the directory slot of its beta string and of its alpha
 //              string (64-bit CAS) and bumps the slot's key count;
-//   2. carve : every used slot takes a power-of-two run of buckets (<= 1 key per 4-slot bucket on
+//              the first key of a string also appends the slot to the list of slots in use;
+//   2. carve : every slot in use takes a power-of-two run of buckets (<= 1 key per 4-slot bucket on
 //              average) from the shared pool with one atomicAdd;
 //   3. fill  : every key inserts (tag, row) into its two regions (32-bit CAS, linear probing
 //              inside the region).
@@ -45,50 +46,69 @@ __global__ void __launch_bounds__(256) index_init_kernel(HashHeader *hdr, uint4 
     hdr->n_keys = N;
     hdr->cursor = 0;
     hdr->pool_buckets = pool_buckets;
+    hdr->n_claimed = 0;
   }
   const size_t slots = (size_t)2 << log2_dir;
   const uint4 empty = make_uint4(0xffffffffu, 0xffffffffu, 0u, 0u);
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < slots; i += (size_t)gridDim.x * blockDim.x) dir[i] = empty;
 }
 
-__device__ __forceinline__ u32 dir_claim(DirSlot *dir, u32 log2_dir, u64 h) {
+__device__ __forceinline__ u32 dir_claim(DirSlot *dir, u32 log2_dir, u64 h, bool &first) {
   const u32 mask = (1u << log2_dir) - 1u;
   u32 s = (u32)(h >> (64 - log2_dir));
   for (;;) {
     const u64 prev = atomicCAS(reinterpret_cast<unsigned long long *>(&dir[s].h), (unsigned long long)kDirEmpty, (unsigned long long)h);
-    if (prev == kDirEmpty || prev == h) return s;
+    first = prev == kDirEmpty;
+    if (first || prev == h) return s;
     s = (s + 1) & mask;
   }
 }
 
+// append `entry` to the list for the lanes with `take` set: one atomicAdd per warp
+__device__ __forceinline__ void list_append(u32 *counter, u32 *list, bool take, u32 entry) {
+  const unsigned m = __ballot_sync(0xffffffffu, take);
+  if (m == 0) return;
+  const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+  u32 base = 0;
+  if (lane == leader) base = atomicAdd(counter, (u32)__popc(m));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  if (take) list[base + __popc(m & ((1u << lane) - 1u))] = entry;
+}
+
 template <int L>
 __global__ void __launch_bounds__(256)
-index_count_kernel(const u64 *__restrict__ key, long long N, HashHeader *hdr, DirSlot *dirB, DirSlot *dirA, u32 *slotB, u32 *slotA) {
+index_count_kernel(const u64 *__restrict__ key, long long N, HashHeader *hdr, DirSlot *dirB, DirSlot *dirA, u32 *slotB, u32 *slotA,
+                   u32 *claimed) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= N) return;
-  const Onv<L> x = load_onv<L>(key + i * L);
-  if (i > 0) {
-    const Onv<L> prev = load_onv<L>(key + (i - 1) * L);
-    if (eq_onv<L>(prev, x)) atomicExch(&hdr->has_dup, 1u);
+  const bool valid = i < N;  // no early return: the list appends are warp-wide
+  bool firstB = false, firstA = false;
+  u32 sb = 0, sa = 0;
+  if (valid) {
+    const Onv<L> x = load_onv<L>(key + i * L);
+    if (i > 0) {
+      const Onv<L> prev = load_onv<L>(key + (i - 1) * L);
+      if (eq_onv<L>(prev, x)) atomicExch(&hdr->has_dup, 1u);
+    }
+    const u32 lg = hdr->log2_dir;
+    sb = dir_claim(dirB, lg, hash_beta<L>(x), firstB);
+    atomicAdd(&dirB[sb].lg, 1u);
+    slotB[i] = sb;
+    sa = dir_claim(dirA, lg, hash_alpha<L>(x), firstA);
+    atomicAdd(&dirA[sa].lg, 1u);
+    slotA[i] = sa;
   }
-  const u32 lg = hdr->log2_dir;
-  const u32 sb = dir_claim(dirB, lg, hash_beta<L>(x));
-  atomicAdd(&dirB[sb].lg, 1u);
-  slotB[i] = sb;
-  const u32 sa = dir_claim(dirA, lg, hash_alpha<L>(x));
-  atomicAdd(&dirA[sa].lg, 1u);
-  slotA[i] = sa;
+  list_append(&hdr->n_claimed, claimed, firstB, sb);
+  list_append(&hdr->n_claimed, claimed, firstA, sa | 0x80000000u);  // bit 31: the alpha-grouped directory
 }
 
 // count -> region: buckets = pow2ceil(count) (< 2 count, so the pool of 4N buckets suffices): at most
 // one key per bucket on average, which keeps overflowed buckets (second probes) below 1 %
-__global__ void __launch_bounds__(256) index_carve_kernel(HashHeader *hdr, DirSlot *dirB, DirSlot *dirA) {
-  const u32 slots = 1u << hdr->log2_dir;
-  for (u32 t = blockIdx.x * blockDim.x + threadIdx.x; t < 2 * slots; t += gridDim.x * blockDim.x) {
-    DirSlot *d = t < slots ? dirB + t : dirA + (t - slots);
-    const u32 c = d->lg;
-    if (d->h == kDirEmpty || c == 0) continue;
-    const u32 want = c;
+__global__ void __launch_bounds__(256) index_carve_kernel(HashHeader *hdr, DirSlot *dirB, DirSlot *dirA, const u32 *__restrict__ claimed) {
+  const u32 n = hdr->n_claimed;
+  for (u32 t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+    const u32 e = claimed[t];
+    DirSlot *d = (e >> 31) ? dirA + (e & 0x7fffffffu) : dirB + e;
+    const u32 want = d->lg;
     u32 lg = 0;
     while ((1u << lg) < want) ++lg;
     d->off = atomicAdd(&hdr->cursor, 1u << lg);
@@ -166,19 +186,20 @@ int launch_hash_build(const u64 *key, long long N, int L, void *ws, long long ws
   u32 *rows = reinterpret_cast<u32 *>(b + l.idx_off);
   u32 *slotB = reinterpret_cast<u32 *>(b + l.scratch_off);
   u32 *slotA = slotB + N;
+  u32 *claimed = slotA + N;
   if (cudaMemsetAsync(pool, 0, (size_t)(l.idx_off - l.pool_off), st) != cudaSuccess) return check_launch("index memset");
   index_init_kernel<<<148 * 8, 256, 0, st>>>(hdr, reinterpret_cast<uint4 *>(dirB), l.log2_dir, (u64)N, (u32)l.pool_buckets);
   count_launch();
   if (N > 0) {
     const unsigned blocks = (unsigned)((N + 255) / 256);
     switch (L) {
-      case 1: index_count_kernel<1><<<blocks, 256, 0, st>>>(key, N, hdr, dirB, dirA, slotB, slotA); break;
-      case 2: index_count_kernel<2><<<blocks, 256, 0, st>>>(key, N, hdr, dirB, dirA, slotB, slotA); break;
-      case 3: index_count_kernel<3><<<blocks, 256, 0, st>>>(key, N, hdr, dirB, dirA, slotB, slotA); break;
+      case 1: index_count_kernel<1><<<blocks, 256, 0, st>>>(key, N, hdr, dirB, dirA, slotB, slotA, claimed); break;
+      case 2: index_count_kernel<2><<<blocks, 256, 0, st>>>(key, N, hdr, dirB, dirA, slotB, slotA, claimed); break;
+      case 3: index_count_kernel<3><<<blocks, 256, 0, st>>>(key, N, hdr, dirB, dirA, slotB, slotA, claimed); break;
       default: set_error("unsupported ONV length L=%d", L); return 1;
     }
     count_launch();
-    index_carve_kernel<<<grid_for(2LL << l.log2_dir, 256, 148LL * 8), 256, 0, st>>>(hdr, dirB, dirA);
+    index_carve_kernel<<<grid_for(2 * N, 256, 148LL * 4), 256, 0, st>>>(hdr, dirB, dirA, claimed);
     count_launch();
     switch (L) {
       case 1: index_fill_kernel<1><<<blocks, 256, 0, st>>>(key, N, dirB, dirA, pool, rows, slotB, slotA); break;

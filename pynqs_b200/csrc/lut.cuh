@@ -30,7 +30,8 @@ struct HashHeader {
   u64 n_keys;
   u32 cursor;    // bump allocator over the shared bucket pool
   u32 pool_buckets;
-  u32 pad[58];
+  u32 n_claimed;  // build: directory slots in use (both directories), the work list of the carve step
+  u32 pad[57];
 };
 static_assert(sizeof(HashHeader) == 256, "header is 256 bytes");
 
@@ -48,7 +49,7 @@ struct __align__(16) DirSlot {
 typedef uint4 TagBucket;  // tag[4]
 typedef uint4 IdxBucket;  // idx[4]
 
-// workspace: header | dir[B] | dir[A] | tag pool (4N + 2 buckets) | idx pool | slot scratch (2N u32)
+// workspace: header | dir[B] | dir[A] | tag pool (4N + 2 buckets) | idx pool | build scratch (4N u32)
 struct IndexLayout {
   u32 log2_dir;
   long long dir_off[2], pool_off, idx_off, scratch_off, total;
@@ -66,7 +67,7 @@ __host__ __device__ inline IndexLayout index_layout(long long N) {
   l.pool_buckets = 4 * N + 2;  // each of the two groupings needs < 2N buckets (<= 1 key per bucket on average)
   l.idx_off = l.pool_off + l.pool_buckets * (long long)sizeof(TagBucket);
   l.scratch_off = l.idx_off + l.pool_buckets * (long long)sizeof(IdxBucket);
-  l.total = l.scratch_off + 2 * N * 4 + 16;
+  l.total = l.scratch_off + 4 * N * 4 + 16;  // per-key slots (2N) + list of claimed slots (<= 2N)
   return l;
 }
 

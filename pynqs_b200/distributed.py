@@ -4,14 +4,16 @@ NVLink on B200, gloo on CPU for tests).
 Replaces the reference's rank-0-centric exchange (vmc/sample.py:627-772: three padded gathers to
 rank 0 -> merge -> two scatters -> two broadcasts with shape handshakes, every wrapper followed by
 a barrier, utils/distributed/comm.py:56-67) by
-  1. one all_gather of the per-rank unique counts,
-  2. one padded all_gather of a packed record {ONV 8L B | psi 8/16 B | count 8 B},
+  1. one all_gather of the per-rank unique counts (skipped when the caller knows they are equal),
+  2. one all_gather per column (ONVs, psi, and the sample counts when there are any) straight into
+     the merged tensors -- no pack / unpack pass,
   3. an identical deterministic merge on every rank (so no broadcast), local slice by
      split_length_idx (utils/public_function.py:720-746),
 and the three collectives of utils/stats/dist_stats.py:18-79 by a single all_reduce of a 5-vector.
 """
 from __future__ import annotations
 
+import math
 from typing import Optional, Tuple
 
 import torch
@@ -40,14 +42,9 @@ def exchange_unique_samples(onv: Tensor, psi: Tensor, counts: Optional[Tensor] =
     rank, world = _world()
     dev = onv.device
     n_r, w = onv.shape
-    if counts is None:
-        counts = torch.ones(n_r, dtype=torch.int64, device=dev)
-    cplx = psi.dtype.is_complex
-    pw = 16 if cplx else 8
-    psi_bytes = torch.view_as_real(psi.to(torch.complex128)).contiguous().view(torch.uint8) if cplx else psi.to(torch.float64).contiguous().view(torch.uint8)
-    rec_w = w + pw + 8
     if world == 1:
-        all_onv, all_psi, all_cnt = onv, psi, counts
+        all_onv, all_psi = onv, psi
+        all_cnt = counts if counts is not None else torch.ones(n_r, dtype=torch.int64, device=dev)
     else:
         if equal_sizes:
             n_list = [n_r] * world
@@ -56,22 +53,26 @@ def exchange_unique_samples(onv: Tensor, psi: Tensor, counts: Optional[Tensor] =
             dist.all_gather_into_tensor(n_all, torch.tensor([n_r], dtype=torch.int64, device=dev))
             n_list = n_all.tolist()
         n_max = max(n_list)
-        rec = torch.zeros((n_max, rec_w), dtype=torch.uint8, device=dev)
-        rec[:n_r, :w] = onv
-        rec[:n_r, w : w + pw] = psi_bytes.view(n_r, pw)
-        rec[:n_r, w + pw :] = counts.to(torch.int64).contiguous().view(torch.uint8).view(n_r, 8)
-        gathered = torch.empty((world * n_max, rec_w), dtype=torch.uint8, device=dev)
-        dist.all_gather_into_tensor(gathered, rec)
-        gathered = gathered.view(world, n_max, rec_w)
-        if min(n_list) == n_max:  # equal pieces: the gathered buffer already is the concatenation
-            cat = gathered.view(world * n_max, rec_w)
+        ragged = min(n_list) != n_max
+
+        def gather(t: Tensor) -> Tensor:
+            """all ranks' rows of t, in rank order; the columns travel as they are (no packing pass)"""
+            t = t.contiguous()
+            if ragged and n_r < n_max:
+                t = torch.cat([t, t.new_zeros((n_max - n_r,) + tuple(t.shape[1:]))])
+            out = torch.empty((world * n_max,) + tuple(t.shape[1:]), dtype=t.dtype, device=dev)
+            dist.all_gather_into_tensor(out, t)
+            if ragged:
+                out = torch.cat([out[r * n_max : r * n_max + n_list[r]] for r in range(world)])
+            return out
+
+        all_onv = gather(onv)
+        if psi.dtype.is_complex:
+            all_psi = torch.view_as_complex(gather(torch.view_as_real(psi)))
         else:
-            cat = torch.cat([gathered[r, : n_list[r]] for r in range(world)])
-        all_onv = cat[:, :w].contiguous()
-        pb = cat[:, w : w + pw].contiguous()
-        all_psi = torch.view_as_complex(pb.view(torch.float64).view(-1, 2)) if cplx else pb.view(torch.float64).view(-1)
-        all_psi = all_psi.to(psi.dtype)
-        all_cnt = cat[:, w + pw :].contiguous().view(torch.int64).view(-1)
+            all_psi = gather(psi)
+        # counts travel only when the caller has them (unit counts otherwise)
+        all_cnt = gather(counts.to(torch.int64)) if counts is not None else torch.ones(all_onv.size(0), dtype=torch.int64, device=dev)
     if disjoint:
         return all_onv, all_psi, all_cnt
     uniq, inv = torch.unique(all_onv, dim=0, return_inverse=True)
@@ -101,46 +102,71 @@ def build_shared_lut(onv: Tensor, psi: Tensor, sorb: int, counts: Optional[Tenso
     return uniq[b:e].contiguous(), prob[b:e] * world, lut
 
 
-def energy_statistics(eloc: Tensor, prob: Tensor, counts: Optional[int] = None) -> dict:
-    """mean / var / sd / se of the local energy -- the quantities of utils/stats/dist_stats.py:18-79
-    (mean = sum_ranks sum_i p_i E_i / W and var = sum_ranks sum_i p_i |mean - E_i|^2 / W with
-    p = prob * W, sample.py:772 + comm.py:65-67) from ONE collective: an all_gather of the per-rank
-    [sum p, local mean, centred second moment, n], combined with the exact identity
-    sum p|E - m|^2 = sum p|E - mu|^2 + (sum p)|mu - m|^2, so there is no cancellation."""
+def _local_moments(e: Tensor, weight: Tensor, amplitude: bool) -> Tensor:
+    """float64[7] = [sum w, sum w Re d, sum w Im d, sum w |d|^2, Re c, Im c, n], d = E - c, c = E[0]:
+    moments about a shift of the size of the values themselves, so the variance has no cancellation.
+    CUDA tensors: one kernel of the library (csrc/table.cu); CPU tensors (gloo tests): torch."""
+    n = e.numel()
+    if e.is_cuda:
+        from .C_extension import weighted_moments
+
+        return weighted_moments(e.contiguous(), weight.contiguous(), amplitude)
+    cplx = e.is_complex()
+    w = (weight.abs() ** 2 if amplitude else weight).to(torch.float64)
+    if n == 0:
+        return torch.zeros(7, dtype=torch.float64)
+    c = e[0]
+    d = e - c
+    if cplx:
+        rows = torch.stack([torch.ones_like(w), d.real, d.imag, d.real * d.real + d.imag * d.imag])
+    else:
+        rows = torch.stack([torch.ones_like(w), d, torch.zeros_like(w), d * d])
+    mom = rows @ w
+    tail = torch.tensor([float(c.real), float(c.imag) if cplx else 0.0, float(n)], dtype=torch.float64)
+    return torch.cat([mom, tail])
+
+
+def _combine_moments(eloc: Tensor, weight: Tensor, amplitude: bool, counts: Optional[int]) -> dict:
     rank, world = _world()
     cplx = eloc.is_complex()
     e = eloc.to(torch.complex128) if cplx else eloc.to(torch.float64)
-    p = prob.to(torch.float64)
-    if e.numel():
-        # one pass: moments of d = E - c about the shift c = E[0] (stable: |d| is of the size of the
-        # spread), then M2 about the local mean mu = c + sum(p d) / w by the same exact identity
-        c = e[0]
-        d = e - c
-        if cplx:
-            rows = torch.stack([torch.ones_like(p), d.real, d.imag, d.real * d.real + d.imag * d.imag])
-        else:
-            rows = torch.stack([torch.ones_like(p), d, torch.zeros_like(p), d * d])
-        mom = rows @ p  # [w, sum p d_re, sum p d_im, sum p |d|^2]
-        w = mom[0]
-        dm_re, dm_im = mom[1] / w, mom[2] / w
-        m2 = mom[3] - w * (dm_re * dm_re + dm_im * dm_im)
-        mu_re = (c.real if cplx else c) + dm_re
-        mu_im = (c.imag + dm_im) if cplx else dm_im
-    else:
-        w = m2 = mu_re = mu_im = torch.zeros((), dtype=torch.float64, device=e.device)
-    vec = torch.stack([w, mu_re, mu_im, m2, torch.tensor(float(e.numel()), dtype=torch.float64, device=e.device)])
+    vec = _local_moments(e, weight if amplitude else weight.to(torch.float64), amplitude)
     if world > 1:
-        allv = torch.empty(world * 5, dtype=torch.float64, device=vec.device)
+        allv = torch.empty(world * 7, dtype=torch.float64, device=vec.device)
         dist.all_gather_into_tensor(allv, vec)
-        allv = allv.view(world, 5)
+        allv = allv.view(world, 7)
     else:
-        allv = vec.view(1, 5)
-    allv = allv.cpu()
-    wr, mr, mi, m2r, nr = allv[:, 0], allv[:, 1], allv[:, 2], allv[:, 3], allv[:, 4]
-    mean_re = float((wr * mr).sum() / world)
-    mean_im = float((wr * mi).sum() / world)
-    var = float((m2r + wr * ((mr - mean_re) ** 2 + (mi - mean_im) ** 2)).sum() / world)
-    n = int(nr.sum()) if counts is None else counts
-    sd = var ** 0.5
+        allv = vec.view(1, 7)
+    rows = allv.tolist()  # the only host synchronisation of the statistics; plain floats from here on
+    z = sum(r[0] for r in rows)
+    # amplitudes: p_i = |psi_i|^2 / Z * W with Z over all ranks (sample.py:772 convention)
+    scale = (world / z if z > 0 else 0.0) if amplitude else 1.0
+    parts = []
+    for w, s_re, s_im, s_sq, c_re, c_im, _n in rows:
+        if w == 0.0:
+            continue
+        dm_re, dm_im = s_re / w, s_im / w
+        parts.append((w * scale, c_re + dm_re, c_im + dm_im, (s_sq - w * (dm_re * dm_re + dm_im * dm_im)) * scale))
+    mean_re = math.fsum(w * mr for w, mr, _, _ in parts) / world
+    mean_im = math.fsum(w * mi for w, _, mi, _ in parts) / world
+    var = math.fsum(m2 + w * ((mr - mean_re) ** 2 + (mi - mean_im) ** 2) for w, mr, mi, m2 in parts) / world
+    n = int(sum(r[6] for r in rows)) if counts is None else counts
+    sd = max(var, 0.0) ** 0.5
     mean = complex(mean_re, mean_im) if cplx else mean_re
-    return {"mean": mean, "var": var, "sd": sd, "se": sd / n ** 0.5, "n": n}
+    return {"mean": mean, "var": var, "sd": sd, "se": sd / n ** 0.5 if n else 0.0, "n": n}
+
+
+def energy_statistics(eloc: Tensor, prob: Tensor, counts: Optional[int] = None) -> dict:
+    """mean / var / sd / se of the local energy -- the quantities of utils/stats/dist_stats.py:18-79
+    (mean = sum_ranks sum_i p_i E_i / W and var = sum_ranks sum_i p_i |mean - E_i|^2 / W with
+    p = prob * W, sample.py:772 + comm.py:65-67) from ONE kernel and ONE collective: an all_gather of
+    the per-rank shifted moments, combined on the host with the exact identity
+    sum p|E - m|^2 = sum p|E - mu|^2 + (sum p)|mu - m|^2."""
+    return _combine_moments(eloc, prob, False, counts)
+
+
+def energy_statistics_amplitudes(eloc: Tensor, psi0: Tensor, counts: Optional[int] = None) -> dict:
+    """Same statistics with p_i = |psi0_i|^2 / Z * W, Z = sum over ALL ranks' rows of |psi0|^2 -- the
+    sample-space probabilities when the ranks' slices partition the unique set (build_shared_lut).
+    Z comes out of the same all_gather, so the probabilities are never materialised."""
+    return _combine_moments(eloc, psi0, True, counts)

@@ -3,7 +3,9 @@
 
 The reference sorts with 8L stable argsorts, one per byte column.  A stable sort by the full
 little-endian multi-word integer gives the identical permutation, so here it is L stable sorts of
-64-bit words (device radix sort), least-significant word first.
+64-bit words, least-significant word first: on CUDA tensors the library's sort_table (radix passes
+over the significant bits only + one gather of keys, values and permutation, csrc/table.cu); on CPU
+tensors (host-side tests, gloo) torch.sort.
 """
 from __future__ import annotations
 
@@ -23,6 +25,10 @@ def sort_onv(bra: Tensor) -> Tensor:
     L = w // 8
     if n == 0:
         return torch.empty(0, dtype=torch.int64, device=bra.device)
+    if bra.is_cuda:
+        from .C_extension import sort_table
+
+        return sort_table(bra.contiguous(), None, 0, want_perm=True)[2]
     words = bra.contiguous().view(torch.int64).view(n, L)
     idx: Optional[Tensor] = None
     for k in range(L):  # least-significant word first (LSD)
@@ -57,9 +63,15 @@ class WavefunctionLUT:
             bra_key = bra_key.to(device)
             wf_value = wf_value.to(device)
         if sort:
-            idx = sort_onv(bra_key)
-            self._bra_key = bra_key[idx].contiguous()
-            self._wf_value = wf_value[idx].contiguous()
+            if bra_key.is_cuda and wf_value.dim() == 1 and wf_value.element_size() in (8, 16):
+                from .C_extension import sort_table
+
+                # ONVs carry no bits at or above sorb, so only ceil(sorb / 8) radix digits are sorted
+                self._bra_key, self._wf_value, idx = sort_table(bra_key.contiguous(), wf_value.contiguous(), sorb)
+            else:
+                idx = sort_onv(bra_key)
+                self._bra_key = bra_key[idx].contiguous()
+                self._wf_value = wf_value[idx].contiguous()
             self._sort_perm = idx
             self._idx_sorted = None  # inverse permutation, built on first use (index_value only)
         else:

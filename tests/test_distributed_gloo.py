@@ -26,7 +26,7 @@ def _worker(rank, world, port, overlap, cplx, q):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        from pynqs_b200.distributed import energy_statistics, exchange_unique_samples, rank_slice
+        from pynqs_b200.distributed import energy_statistics, energy_statistics_amplitudes, exchange_unique_samples, rank_slice
 
         keys = S.random_onvs(1000, 40, 15, 15, seed=100)
         psi_all = S.random_psi(1000, seed=101, complex_=cplx)
@@ -48,7 +48,12 @@ def _worker(rank, world, port, overlap, cplx, q):
             eloc_all = eloc_all + 1j * rng.standard_normal(uniq.size(0)) * 1e-3
         prob_all = cnt.numpy() / cnt.numpy().sum()
         st = energy_statistics(torch.from_numpy(eloc_all[b:e]), torch.from_numpy(prob_all[b:e]) * world)
-        q.put((rank, uniq.numpy(), wf.numpy(), cnt.numpy(), (b, e), st))
+        st_amp = energy_statistics_amplitudes(torch.from_numpy(eloc_all[b:e]), wf[b:e].contiguous())
+        # equal pieces without counts: no size handshake, unit counts
+        u2, w2, c2 = exchange_unique_samples(onv[:300].contiguous(), psi[:300].contiguous(), None, disjoint=True, equal_sizes=True)
+        assert u2.shape == (300 * world, onv.size(1)) and torch.equal(u2[300 * rank : 300 * (rank + 1)], onv[:300])
+        assert torch.equal(w2[300 * rank : 300 * (rank + 1)], psi[:300]) and int(c2.sum()) == 300 * world
+        q.put((rank, uniq.numpy(), wf.numpy(), cnt.numpy(), (b, e), st, st_amp))
     finally:
         dist.destroy_process_group()
 
@@ -97,7 +102,11 @@ def test_exchange_and_statistics(world, overlap, cplx):
     mean = np.sum(prob_all * eloc_all)
     var = np.sum(prob_all * np.abs(eloc_all - mean) ** 2)
     covered = []
-    for rank, uniq, wf, cnt, (b, e), st in res:
+    p_amp = np.abs(want_psi) ** 2 / np.sum(np.abs(want_psi) ** 2)
+    mean_amp = np.sum(p_amp * eloc_all)
+    var_amp = np.sum(p_amp * np.abs(eloc_all - mean_amp) ** 2)
+    for rank, uniq, wf, cnt, (b, e), st, st_amp in res:
+        assert abs(st_amp["mean"] - mean_amp) < 1e-12 and abs(st_amp["var"] - var_amp) < 1e-12 * max(1.0, var_amp)
         np.testing.assert_array_equal(uniq, want_keys)      # every rank holds the identical table
         np.testing.assert_array_equal(wf, want_psi)
         np.testing.assert_array_equal(cnt, want_cnt)

@@ -377,3 +377,63 @@ def test_192_sorb_three_words_against_oracle():
         comb, hmat = ops.get_comb_hij_fused(dev(bra), dev(h1e_np), h2e, sorb, 8, noA, noB, prepared=prepared)
         np.testing.assert_array_equal(comb.cpu().numpy(), want_c)
         np.testing.assert_array_equal(hmat.cpu().numpy(), want_h)
+
+
+# ---- the steps either side of the kernels: table sort, energy moments -------------------------------
+@pytest.mark.parametrize("L,sorb,na,cplx", [(1, 40, 15, False), (1, 64, 20, True), (2, 100, 25, True), (3, 132, 3, False), (3, 192, 40, True)])
+def test_sort_table_matches_oracle_order(L, sorb, na, cplx):
+    """sort_table on the significant bits == the reference's lexsort order (stable: duplicates stay
+    in input order), keys / values / permutation all consistent."""
+    k = S.random_onvs(3000, sorb, na, na, seed=70 + L)
+    k = np.concatenate([k, k[:500]])[np.random.default_rng(6).permutation(3500)]
+    psi = S.random_psi(3500, seed=71, complex_=cplx)
+    order = O.sort_onv(k)
+    for bits in (sorb, 0):
+        sk, sp, perm = ops.sort_table(dev(k), dev(psi), bits)
+        np.testing.assert_array_equal(perm.cpu().numpy(), order)
+        np.testing.assert_array_equal(sk.cpu().numpy(), k[order])
+        np.testing.assert_array_equal(sp.cpu().numpy(), psi[order])
+    lut = WavefunctionLUT(dev(k[:3000]), dev(psi[:3000]), sorb, DEV, rank=0, world_size=1)
+    o3 = O.sort_onv(k[:3000])
+    np.testing.assert_array_equal(lut.bra_key.cpu().numpy(), k[:3000][o3])
+    np.testing.assert_array_equal(lut.wf_value.cpu().numpy(), psi[:3000][o3])
+    inv = np.empty(3000, dtype=np.int64)
+    inv[o3] = np.arange(3000)
+    np.testing.assert_array_equal(lut.idx_sorted.cpu().numpy(), inv)
+
+
+def test_sort_table_one_million_keys_sorted_and_a_permutation():
+    k = S.random_onvs(1_000_000, 40, 15, 15, seed=72)
+    psi = S.random_psi(1_000_000, seed=73)
+    sk, sp, perm = ops.sort_table(dev(k), dev(psi), 40)
+    w = sk.view(torch.int64).view(-1)
+    assert bool((w[1:] > w[:-1]).all())  # strictly ascending: sorted and unique
+    assert torch.equal(torch.sort(perm).values, torch.arange(1_000_000, device=DEV))
+    assert torch.equal(dev(k)[perm], sk) and torch.equal(dev(psi)[perm], sp)
+    e, _, e_perm = ops.sort_table(dev(k[:0]), None, 40)
+    assert e.shape == (0, 8) and e_perm.numel() == 0
+
+
+@pytest.mark.parametrize("n", [1, 31, 1000, 300_001])
+@pytest.mark.parametrize("cplx", [False, True])
+def test_weighted_moments_and_statistics(n, cplx):
+    from pynqs_b200.distributed import energy_statistics, energy_statistics_amplitudes
+
+    rng = np.random.default_rng(80 + n)
+    e = rng.standard_normal(n) - 116.6
+    if cplx:
+        e = e + 1e-3j * rng.standard_normal(n)
+    amp = S.random_psi(n, seed=81, complex_=cplx)
+    w = np.abs(amp) ** 2
+    for weight, is_amp in ((dev(w), False), (dev(amp), True)):
+        m = ops.weighted_moments(dev(e), weight, is_amp).cpu().numpy()
+        d = e - e[0]
+        want = [w.sum(), (w * d.real).sum(), (w * d.imag).sum(), (w * np.abs(d) ** 2).sum(), e[0].real, e[0].imag, n]
+        np.testing.assert_allclose(m, want, rtol=1e-12, atol=1e-12 * w.sum())
+        m2 = ops.weighted_moments(dev(e), weight, is_amp).cpu().numpy()
+        np.testing.assert_array_equal(m, m2)  # deterministic, and the ticket was reset
+    p = w / w.sum()
+    mean = (p * e).sum()
+    var = (p * np.abs(e - mean) ** 2).sum()
+    for st in (energy_statistics(dev(e), dev(p)), energy_statistics_amplitudes(dev(e), dev(amp))):
+        assert abs(st["mean"] - mean) < 1e-11 and abs(st["var"] - var) < 1e-11 * max(1.0, var) and st["n"] == n
