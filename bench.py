@@ -261,11 +261,12 @@ def run_ours(args):
         uniq, wf, cnt = exchange_unique_samples(k, p, None, disjoint=True, equal_sizes=equal_sizes)
         ev[1].record()
         lut = WavefunctionLUT(uniq, wf, SORB, dev, sort=not args.unsorted_table, rank=rank, world_size=world)
+        gidx = lut.group_index  # built here, inside the table phase
         b, e = rank_slice(uniq.size(0), rank, world)
         x = uniq[b:e]
         e0, e1 = ev[2], ev[3]
         e0.record()
-        eloc, psi0 = ops.eloc_sample_space(x, h1e, h2e, SORB, NELE, NOA, NOB, lut.bra_key, lut.wf_value, lut.hash_index)
+        eloc, psi0 = ops.eloc_sample_space(x, h1e, h2e, SORB, NELE, NOA, NOB, lut.bra_key, lut.wf_value, gidx)
         e1.record()
         # p_i = |psi_i|^2 / sum_table |psi|^2 * world (reference convention, sample.py:772); the ranks' slices
         # partition the table, so the norm comes out of the statistics' own all-gather

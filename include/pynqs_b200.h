@@ -99,24 +99,30 @@ int pynqs_hij(const uint8_t *bra, const uint8_t *ket, const void *h1e, const voi
 int pynqs_lut(const uint8_t *key, int64_t N, const uint8_t *onv, int64_t n, int L, int64_t *idx, uint8_t *mask,
               void *stream);
 
-/* Hash index over a sorted UNIQUE key table -- an internal accelerator for the two functions
- * below; results are identical to pynqs_lut.  If the table holds duplicates the build records
+/* Hash index over a sorted UNIQUE key table -- an internal accelerator of pynqs_lut_hashed;
+ * results are identical to pynqs_lut.  If the table holds duplicates the build records
  * it and the lookups fall back to the classic search on the device (no host round trip). */
 int pynqs_hash_bytes(int64_t N, int L, int64_t *bytes);
 int pynqs_hash_build(const uint8_t *key, int64_t N, int L, void *hash_ws, int64_t hash_bytes, void *stream);
 int pynqs_lut_hashed(const uint8_t *key, int64_t N, const uint8_t *onv, int64_t n, int L, const void *hash_ws,
                      int64_t *idx, uint8_t *mask, void *stream);
 
+/* String-grouped copies of a sorted key table (the keys bucketed by the hash of their beta string
+ * and, a second time, of their alpha string) -- what pynqs_eloc_sample_space scans.  If the table
+ * holds duplicates the build records it and the local-energy kernels take the classic search. */
+int pynqs_group_bytes(int64_t N, int L, int64_t *bytes);
+int pynqs_group_build(const uint8_t *key, int64_t N, int L, void *group_ws, int64_t group_bytes, void *stream);
+
 /* Additive op: the whole sample-space local energy of vmc/energy/eloc.py:326-397 in one pass,
  * never materialising comb / Hmat:  for each sample x, psi0 = table value of x (0 if absent),
  *   eloc = sum over x' in {x} U SD(x) found in the table of (psi(x') / psi0) * <x|H|x'>.
  * psi: double[N] (psi_complex == 0) or interleaved complex128[N]; eloc / psi0 likewise [n].
  * scratch: pynqs_eloc_scratch_bytes(n, ...) bytes.  h1e/h2e are the packed float64 arrays.
- * hash_ws must have been built by pynqs_hash_build for exactly this key table. */
+ * group_ws must have been built by pynqs_group_build for exactly this key table. */
 int pynqs_eloc_scratch_bytes(int64_t n, int sorb, int noA, int noB, int psi_complex, int64_t *bytes);
 int pynqs_eloc_sample_space(const uint8_t *bra, int64_t n, const double *h1e, const double *h2e, int sorb,
                             int nele, int noA, int noB, const uint8_t *key, const void *psi, int psi_complex,
-                            int64_t N, const void *hash_ws, void *scratch, int64_t scratch_bytes, void *eloc,
+                            int64_t N, const void *group_ws, void *scratch, int64_t scratch_bytes, void *eloc,
                             void *psi0, void *stream);
 
 /* ---- unique-sample table: sort (utils/public_function.py:626-689, 754-788) ----------------------

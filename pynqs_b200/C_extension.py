@@ -313,6 +313,47 @@ def _cached_hash(bra_key: Tensor) -> HashIndex:
     return hidx
 
 
+# ---- string-grouped copies of a sorted key table (what the local-energy kernels scan) ----------------
+class GroupIndex:
+    """The key table bucketed by the hash of the beta string and, a second time, of the alpha string
+    (csrc/gindex.cuh); internal to eloc_sample_space."""
+
+    def __init__(self, bra_key: Tensor):
+        dev = _need_cuda(bra_key)
+        _contig(bra_key, "bra_key")
+        self.L = _onv_words(bra_key, "bra_key")
+        self.N = bra_key.size(0)
+        nbytes = _lib.ctypes.c_int64()
+        _lib.check(_lib.load().pynqs_group_bytes(i64(self.N), self.L, _lib.ctypes.byref(nbytes)))
+        self.workspace = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(
+                _lib.load().pynqs_group_build(
+                    vp(bra_key.data_ptr()), i64(self.N), self.L, vp(self.workspace.data_ptr()), i64(nbytes.value), _stream(dev)
+                )
+            )
+
+    @property
+    def nbytes(self) -> int:
+        return self.workspace.numel()
+
+
+_group_cache: dict = {}
+
+
+def _cached_group(bra_key: Tensor) -> GroupIndex:
+    """Per-tensor-object cache: valid while the same tensor object is alive and unmodified."""
+    k = id(bra_key)
+    ent = _group_cache.get(k)
+    if ent is not None:
+        ref, version, ptr, gidx = ent
+        if ref() is bra_key and version == bra_key._version and ptr == bra_key.data_ptr():
+            return gidx
+    gidx = GroupIndex(bra_key)
+    _group_cache[k] = (weakref.ref(bra_key, lambda _r, k=k: _group_cache.pop(k, None)), bra_key._version, bra_key.data_ptr(), gidx)
+    return gidx
+
+
 def wavefunction_lut(bra_key: Tensor, onv: Tensor, sorb: int, little_endian: bool = True, *, hash_index: HashIndex | None = None) -> Tuple[Tensor, Tensor]:
     """Index of every onv row in the sorted key table (C_extension.pyi:305-357): (idx int64 [n]
     with -1 for absent rows, mask bool [n]).  The ONV width comes from the tensors, not from
@@ -350,7 +391,7 @@ def wavefunction_lut(bra_key: Tensor, onv: Tensor, sorb: int, little_endian: boo
 
 def eloc_sample_space(
     bra: Tensor, h1e: Tensor, h2e: Tensor, sorb: int, nele: int, noA: int, noB: int,
-    bra_key: Tensor, wf_value: Tensor, hash_index: HashIndex | None = None,
+    bra_key: Tensor, wf_value: Tensor, group_index: GroupIndex | None = None,
 ) -> Tuple[Tensor, Tensor]:
     """Additive op: the whole sample-space local energy of vmc/energy/eloc.py:326-397 in one pass.
     Returns (eloc [n], psi0 [n]) in wf_value's dtype (float64 or complex128).  bra_key must be the
@@ -372,8 +413,10 @@ def eloc_sample_space(
     psi0 = torch.empty(n, dtype=wf_value.dtype, device=dev)
     if n == 0:
         return eloc, psi0
-    if hash_index is None:
-        hash_index = _cached_hash(bra_key)
+    if group_index is None:
+        group_index = _cached_group(bra_key)
+    if group_index.N != N or group_index.L != L:
+        raise ValueError("group_index was built for another key table")
     lib = _lib.load()
     nbytes = _lib.ctypes.c_int64()
     _lib.check(lib.pynqs_eloc_scratch_bytes(i64(n), int(sorb), int(noA), int(noB), cplx, _lib.ctypes.byref(nbytes)))
@@ -382,7 +425,7 @@ def eloc_sample_space(
         _lib.check(
             lib.pynqs_eloc_sample_space(
                 vp(bra.data_ptr()), i64(n), vp(h1e.data_ptr()), vp(h2e.data_ptr()), int(sorb), int(nele), int(noA), int(noB),
-                vp(bra_key.data_ptr()), vp(wf_value.data_ptr()), cplx, i64(N), vp(hash_index.workspace.data_ptr()),
+                vp(bra_key.data_ptr()), vp(wf_value.data_ptr()), cplx, i64(N), vp(group_index.workspace.data_ptr()),
                 vp(scratch.data_ptr()), i64(nbytes.value), vp(eloc.data_ptr()), vp(psi0.data_ptr()), _stream(dev),
             )
         )

@@ -14,7 +14,7 @@ SYMBOLS = [
     "pynqs_tensor_to_onv", "pynqs_onv_to_tensor", "pynqs_comb", "pynqs_prepared_bytes", "pynqs_prepare_integrals",
     "pynqs_comb_hij_fused", "pynqs_hij",
     "pynqs_lut", "pynqs_hash_bytes", "pynqs_hash_build", "pynqs_lut_hashed",
-    "pynqs_eloc_scratch_bytes", "pynqs_eloc_sample_space",
+    "pynqs_group_bytes", "pynqs_group_build", "pynqs_eloc_scratch_bytes", "pynqs_eloc_sample_space",
     "pynqs_sort_bytes", "pynqs_sort_table", "pynqs_moments_scratch_bytes", "pynqs_weighted_moments",
     "pynqs_launch_count",
 ]

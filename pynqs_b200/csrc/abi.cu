@@ -46,7 +46,9 @@ int launch_lut_classic(const u64 *, long long, const u64 *, long long, int, long
 long long hash_workspace_bytes(long long);
 int launch_hash_build(const u64 *, long long, int, void *, long long, cudaStream_t);
 int launch_lut_hashed(const u64 *, long long, const u64 *, long long, int, const void *, long long *, unsigned char *, cudaStream_t);
-long long eloc_scratch_bytes(long long, int, int);
+long long eloc_scratch_bytes(long long, const ExcGeom &);
+long long group_workspace_bytes(long long, int);
+int launch_group_build(const u64 *, long long, int, void *, long long, cudaStream_t);
 int launch_eloc(const u64 *, long long, const double *, const double *, const u64 *, const double *, int, long long,
                 const void *, void *, long long, double *, double *, const ExcGeom &, cudaStream_t);
 long long sort_workspace_bytes(long long);
@@ -239,24 +241,40 @@ int pynqs_lut_hashed(const uint8_t *key, int64_t N, const uint8_t *onv, int64_t 
                            reinterpret_cast<long long *>(idx), mask, (cudaStream_t)stream);
 }
 
+int pynqs_group_bytes(int64_t N, int L, int64_t *bytes) {
+  if (int rc = check_L(L)) return rc;
+  if (N < 0 || N >= (1LL << 31)) {
+    set_error("the grouped table supports 0 <= N < 2^31 keys (got %lld)", (long long)N);
+    return PYNQS_EVALUE;
+  }
+  *bytes = group_workspace_bytes(N, L);
+  return 0;
+}
+
+int pynqs_group_build(const uint8_t *key, int64_t N, int L, void *group_ws, int64_t group_bytes, void *stream) {
+  if (int rc = check_L(L)) return rc;
+  return launch_group_build(reinterpret_cast<const u64 *>(key), N, L, group_ws, group_bytes, (cudaStream_t)stream);
+}
+
 int pynqs_eloc_scratch_bytes(int64_t n, int sorb, int noA, int noB, int psi_complex, int64_t *bytes) {
   if (int rc = check_geometry(sorb, 0, noA, noB)) return rc;
   long long nsd;
   if (int rc = num_sd_checked(sorb, noA, noB, &nsd)) return rc;
-  *bytes = eloc_scratch_bytes(n, (int)nsd, psi_complex);
+  (void)psi_complex;
+  *bytes = eloc_scratch_bytes(n, make_geom(sorb, noA + noB, noA, noB));
   return 0;
 }
 
 int pynqs_eloc_sample_space(const uint8_t *bra, int64_t n, const double *h1e, const double *h2e, int sorb, int nele,
                             int noA, int noB, const uint8_t *key, const void *psi, int psi_complex, int64_t N,
-                            const void *hash_ws, void *scratch, int64_t scratch_bytes, void *eloc, void *psi0,
+                            const void *group_ws, void *scratch, int64_t scratch_bytes, void *eloc, void *psi0,
                             void *stream) {
   if (int rc = check_geometry(sorb, nele, noA, noB)) return rc;
   long long nsd;
   if (int rc = num_sd_checked(sorb, noA, noB, &nsd)) return rc;
   const ExcGeom g = make_geom(sorb, nele, noA, noB);
   return launch_eloc(reinterpret_cast<const u64 *>(bra), n, h1e, h2e, reinterpret_cast<const u64 *>(key),
-                     (const double *)psi, psi_complex, N, hash_ws, scratch, scratch_bytes, (double *)eloc, (double *)psi0, g,
+                     (const double *)psi, psi_complex, N, group_ws, scratch, scratch_bytes, (double *)eloc, (double *)psi0, g,
                      (cudaStream_t)stream);
 }
 

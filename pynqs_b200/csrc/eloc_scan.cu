@@ -1,0 +1,555 @@
+// eloc_scan.cu -- sample-space local energy without materialising comb / Hmat.
+//
+// Replaces what the reference does in three native calls plus ~6 torch passes over [n, M]
+// (vmc/energy/eloc.py:326-397: get_comb_hij_fused -> WavefunctionLUT.lookup -> scatter ->
+// divide -> multiply -> sum).  Nothing of size [n, M] ever reaches HBM, and the connected
+// determinants are never formed: the kernels walk the string-grouped copies of the table
+// (gindex.cuh) and pick out, with XOR + popcount, the keys that ARE connected to the sample.
+//
+//   eloc_scan_kernel   one CTA per (sample, slice of its groups).  Groups of a sample x:
+//         g < sB : the bucket of the beta string of x's g-th beta single; a key there is an
+//                  alpha-beta double of x iff its beta part equals that string and its alpha part
+//                  is at distance 2 from x's;
+//         g = sB : the bucket of x's own beta string: alpha singles (distance 2), alpha-alpha
+//                  doubles (4) and x itself (0);
+//         g = sB+1: the bucket of x's own alpha string: beta singles and beta-beta doubles.
+//       A warp takes a group at a time, lanes take consecutive keys: coalesced loads, ~10
+//       instructions per key, no hashing and no searching.  Buckets much larger than the number of
+//       determinants they could contain are searched instead (binary search inside the bucket, the
+//       reference's own algorithm on a short range).  Hits go to per-warp queues (ballot + popcount
+//       compaction) and from there to a global candidate buffer in a deterministic order.
+//   eloc_eval_kernel   one warp per sample: for every hit, <x|H|x'> re-derived from the two bit
+//       strings (rederive.cuh: same arithmetic, same order of additions as the fused operator)
+//       times psi(x') / psi(x), summed over a fixed lane assignment and a shuffle tree.
+//
+// Exactness: a key is a hit iff it is one of the reference's connected determinants and is in the
+// table -- the same set binary_search_BigInteger would find.  Tables with duplicate keys, and
+// samples whose hits overflow the queues, take the reference's route instead (enumerate every
+// excitation, classic binary search); no floating point atomics anywhere.
+#include "gindex.cuh"
+#include "lut.cuh"
+#include "rederive.cuh"
+#include "tables.cuh"
+
+namespace pynqs {
+
+constexpr int kScanThreads = 256;  // scan kernel: 8 warps per CTA
+constexpr int kScanWarps = kScanThreads / 32;
+constexpr int kQueue = 512;        // hits per warp before the sample falls back to the full route
+constexpr int kEvalThreads = 128;  // eval kernel: 4 samples per CTA
+constexpr u32 kOverflow = 0x80000000u;
+constexpr u32 kNoSelf = 0xffffffffu;
+
+struct Cplx {
+  double re, im;
+};
+
+// numpy / c10 complex division (torch/headeronly/util/complex.h operator/=)
+__device__ __forceinline__ Cplx cdiv(Cplx x, Cplx y) {
+  const double a = x.re, b = x.im, c = y.re, d = y.im;
+  const double ac = fabs(c), ad = fabs(d);
+  Cplx r;
+  if (ac >= ad) {
+    if (ac == 0.0 && ad == 0.0) {
+      r.re = a / ac;
+      r.im = b / ad;
+    } else {
+      const double rat = d / c, scl = 1.0 / (c + d * rat);
+      r.re = (a + b * rat) * scl;
+      r.im = (b - a * rat) * scl;
+    }
+  } else {
+    const double rat = c / d, scl = 1.0 / (d + c * rat);
+    r.re = (a * rat + b) * scl;
+    r.im = (b * rat - a) * scl;
+  }
+  return r;
+}
+
+template <bool CPLX>
+__device__ __forceinline__ Cplx load_psi(const double *__restrict__ psi, long long id) {
+  Cplx v;
+  if (CPLX) {
+    const double2 t = __ldg(reinterpret_cast<const double2 *>(psi) + id);
+    v.re = t.x;
+    v.im = t.y;
+  } else {
+    v.re = __ldg(psi + id);
+    v.im = 0.0;
+  }
+  return v;
+}
+
+// ratio psi'/psi0 times a real H, accumulated
+template <bool CPLX>
+__device__ __forceinline__ void accumulate(Cplx &acc, Cplx pm, Cplx p0, double h) {
+  if (CPLX) {
+    const Cplx q = cdiv(pm, p0);
+    acc.re += q.re * h;
+    acc.im += q.im * h;
+  } else {
+    acc.re += (pm.re / p0.re) * h;
+  }
+}
+
+// the entry's two orbitals as an excitation mask (L = 1) or packed o0 | o1 << 8 (L > 1)
+template <int L>
+__device__ __forceinline__ u64 msk_make(u32 o0, u32 o1) {
+  return L == 1 ? ((1ull << o0) | (1ull << o1)) : (u64)(o0 | (o1 << 8));
+}
+template <int L>
+__device__ __forceinline__ Onv<L> msk_apply(const Onv<L> &x, u64 m) {
+  Onv<L> y = x;
+  if (L == 1) {
+    y.w[0] ^= m;
+  } else {
+    flip_bit<L>(y, (int)(m & 0xffu));
+    flip_bit<L>(y, (int)((m >> 8) & 0xffu));
+  }
+  return y;
+}
+
+// per (sample, slice, warp) run of hits in the global buffer
+struct HitRun {
+  u32 off, cnt;  // cnt & kOverflow: a queue or the buffer overflowed -> the sample takes the full route
+};
+
+// hit = position in the grouped copy | grouping << 31
+__device__ __forceinline__ void push_hits(u32 *queue, u32 &qn, bool hit, u32 value) {
+  const u32 m = __ballot_sync(0xffffffffu, hit);
+  if (m == 0) return;
+  if (hit) {
+    const u32 at = qn + (u32)__popc(m & ((1u << (threadIdx.x & 31)) - 1u));
+    if (at < (u32)kQueue) queue[at] = value;
+  }
+  qn += (u32)__popc(m);
+}
+
+// distance test of one key against the pattern y: `same` = the bits that must agree (the string that
+// defines the group).  Returns the popcount of the difference, or 255 when the strings differ.
+template <int L>
+__device__ __forceinline__ u32 key_distance(const Onv<L> &k, const Onv<L> &y, u64 same) {
+  u32 pc = 0;
+  u64 bad = 0;
+#pragma unroll
+  for (int i = 0; i < L; ++i) {
+    const u64 d = k.w[i] ^ y.w[i];
+    bad |= d & same;
+    pc += (u32)__popcll(d);
+  }
+  return bad ? 255u : pc;
+}
+
+// scan the keys [s, e) of one bucket: two keys per lane in flight
+template <int L>
+__device__ __forceinline__ void scan_bucket(const u64 *__restrict__ keys, u32 s, u32 e, const Onv<L> &y, u64 same, u32 allow, u32 gbit,
+                                            u32 *queue, u32 &qn, u32 *self_pos) {
+  const u32 lane = threadIdx.x & 31;
+  for (u32 k0 = s; k0 < e; k0 += 64) {
+    const u32 p0 = k0 + lane, p1 = p0 + 32;
+    u32 d0 = 255u, d1 = 255u;
+    Onv<L> a, b;
+    if (p0 < e) a = load_onv<L>(keys + (size_t)p0 * L);
+    if (p1 < e) b = load_onv<L>(keys + (size_t)p1 * L);
+    if (p0 < e) d0 = key_distance<L>(a, y, same);
+    if (p1 < e) d1 = key_distance<L>(b, y, same);
+    if (self_pos != nullptr) {  // the sample itself (own beta bucket only)
+      if (d0 == 0u) *self_pos = p0;
+      if (d1 == 0u) *self_pos = p1;
+    }
+    push_hits(queue, qn, d0 < 8u && ((allow >> d0) & 1u), p0 | gbit);
+    push_hits(queue, qn, d1 < 8u && ((allow >> d1) & 1u), p1 | gbit);
+  }
+}
+
+// large bucket: search each determinant the group could contain (targets enumerated by the lanes)
+//   kind 0: alpha-beta doubles on top of a beta single, base = x with that single applied (targets: sA alpha singles)
+//   kind 1: own beta string  (targets: x itself, sA alpha singles, noAA * nvAA alpha-alpha doubles)
+//   kind 2: own alpha string (targets: sB beta singles, noBB * nvBB beta-beta doubles)
+struct SearchGeom {  // per kind: number of single targets, hole pairs, particle pairs and their table offsets
+  int nS, nH, nP, oS, oH, oP, self, pad;
+};
+
+template <int L>
+__device__ __noinline__ u32 search_bucket(const u64 *__restrict__ keys, u32 s, u32 e, const Onv<L> base, const u64 *msk,
+                                          const SearchGeom *sg, u32 gbit, u32 *queue, u32 qn, u32 *self_pos) {
+  const int lane = threadIdx.x & 31;
+  const int nS = sg->nS, nH = sg->nH, nD = nH * sg->nP, oS = sg->oS, oH = sg->oH, oP = sg->oP;
+  const int total = nS + nD + sg->self;
+  for (int t0 = 0; t0 < total; t0 += 32) {
+    const int t = t0 + lane;
+    u32 pos = 0xffffffffu;
+    bool self = false;
+    if (t < total) {
+      Onv<L> y = base;
+      if (t < nS) {
+        y = msk_apply<L>(y, msk[oS + t]);
+      } else if (t < nS + nD) {
+        const int u = t - nS, pp = u / nH, hp = u - pp * nH;
+        y = msk_apply<L>(msk_apply<L>(y, msk[oH + hp]), msk[oP + pp]);
+      } else {
+        self = true;
+      }
+      pos = bucket_search<L>(keys, s, e, y);
+    }
+    if (self && pos != 0xffffffffu) {
+      *self_pos = pos;
+      pos = 0xffffffffu;
+    }
+    push_hits(queue, qn, pos != 0xffffffffu, pos | gbit);
+  }
+  return qn;
+}
+
+// dynamic shared memory of the scan kernel: lists | patterns | tables | buckets | chunk list | queues
+constexpr int kListChunksDecl = 4;
+__host__ __device__ inline size_t scan_queue_offset(const ExcGeom &g) {
+  const size_t sB = (size_t)g.noB * g.nvB, nG = sB + 2;
+  size_t o = sizeof(OrbLists) + 8 * nG * g.L + 8 * (size_t)table_offsets(g).total + 8 * nG;
+  o = ((o + 15) & ~(size_t)15) + 16 * (sB * kListChunksDecl + 8);
+  return (o + 15) & ~(size_t)15;
+}
+
+// groups of at most kListChunks * 32 keys are cut into 32-key chunks and all chunks of a sample are
+// processed as one flat, evenly divided list (a warp would otherwise idle on its small groups while
+// another one walks a large group); larger groups are walked (or searched) by one warp each.
+constexpr int kListChunks = kListChunksDecl;
+constexpr int kChunkUnroll = 4;  // independent key loads in flight per lane
+
+template <int L>
+__global__ void __launch_bounds__(kScanThreads)
+eloc_scan_kernel(const u64 *__restrict__ bra, long long n, GroupView gv, HitRun *__restrict__ runs, u32 *__restrict__ hits,
+                 u32 *__restrict__ self_pos, u32 *cursor, u32 hit_cap, int splits, ExcGeom g) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const TableOffsets to = table_offsets(g);
+  const int sB = g.noB * g.nvB, nG = sB + 2;
+  OrbLists &lists = *reinterpret_cast<OrbLists *>(smem_raw);
+  u64 *ypat = reinterpret_cast<u64 *>(smem_raw + sizeof(OrbLists));  // [nG][L] pattern of every group
+  u64 *msk = ypat + (size_t)nG * L;                                   // excitation tables (search route only)
+  uint2 *rng = reinterpret_cast<uint2 *>(msk + to.total);             // [nG] bucket of every group
+  // chunk list: {first key, bucket end, pattern (L = 1) or group (L > 1)} -- one 16-byte load per chunk
+  uint4 *clist = reinterpret_cast<uint4 *>(smem_raw + scan_queue_offset(g)) - ((size_t)sB * kListChunks + 8);
+  u32 *queues = reinterpret_cast<u32 *>(smem_raw + scan_queue_offset(g));
+  __shared__ int s_nchunks;
+  __shared__ SearchGeom s_sg[3];
+  if (threadIdx.x == 0) {
+    s_sg[0] = SearchGeom{g.sA, 0, 0, to.sa, 0, 0, 0, 0};
+    s_sg[1] = SearchGeom{g.sA, g.noAA, g.nvAA, to.sa, to.hpa, to.ppa, 1, 0};
+    s_sg[2] = SearchGeom{sB, g.noBB, g.nvBB, to.sb, to.hpb, to.ppb, 0, 0};
+  }
+
+  const long long s = splits == 1 ? (long long)blockIdx.x : (long long)(blockIdx.x / (unsigned)splits);
+  const int split = splits == 1 ? 0 : (int)(blockIdx.x - (unsigned)s * (unsigned)splits);
+  if (s >= n) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  HitRun *my_run = runs + (s * splits + split) * kScanWarps + warp;
+  if (gv.hdr->has_dup) {  // duplicate keys: the eval kernel takes the reference's route for every sample
+    if (lane == 0) {
+      const HitRun run = {0u, kOverflow};
+      *my_run = run;
+    }
+    return;
+  }
+  const Onv<L> x = load_onv<L>(bra + s * L);
+  if (threadIdx.x < 32) build_lists<L>(x, g.sorb, g.noA, g.noB, lists, threadIdx.x);
+  __syncthreads();
+
+  // the groups of this slice: pattern and bucket of each
+  const int per = (nG + splits - 1) / splits;
+  const int g_begin = split * per, g_end = min(nG, g_begin + per), ab_end = min(g_end, sB);
+  const u32 big_ab = 16u * (u32)g.sA;  // an alpha-beta group this large is searched, not walked
+  bool need_tables = false;
+  for (int q = g_begin + (int)threadIdx.x; q < g_end; q += kScanThreads) {
+    Onv<L> y = x;
+    if (q < sB) {  // beta single q: hole = q % noB, particle = q / noB of the merged beta list
+      const u32 pb = fdiv((u32)q, g.by_noB), hb = (u32)q - pb * g.noB;
+      flip_bit<L>(y, lists.b[hb] & 0xff);
+      flip_bit<L>(y, lists.b[g.noB + pb] & 0xff);
+    }
+    const int grouping = q == sB + 1 ? 1 : 0;
+    const u32 *st = (grouping ? gv.start[1] : gv.start[0]) + group_bucket<L>(y, grouping, gv.shift);  // no dynamic index into the param struct
+    const uint2 r = make_uint2(__ldg(st), __ldg(st + 1));
+    rng[q] = r;
+#pragma unroll
+    for (int w = 0; w < L; ++w) ypat[q * L + w] = y.w[w];
+    const u32 size = r.y - r.x;
+    if (q < sB) need_tables |= size > big_ab;
+    else if (q == sB) need_tables |= size > 16u * (u32)(g.sA + g.noAA * g.nvAA + 1);
+    else need_tables |= size > 16u * (u32)(sB + g.noBB * g.nvBB);
+  }
+  need_tables = __syncthreads_or((int)need_tables) != 0;
+  if (need_tables) {
+    for_each_table_entry(g, lists, to, [&](int t, int, u32 e0, u32 e1) { msk[t] = msk_make<L>(e0 & 0xffu, e1 & 0xffu); });
+  }
+  if (warp == 0) {  // chunk list of the small alpha-beta groups, in group order
+    u32 base = 0;
+    for (int q0 = g_begin; q0 < ab_end; q0 += 32) {
+      const int q = q0 + lane;
+      u32 nc = 0;
+      uint4 ent = make_uint4(0u, 0u, (u32)q, 0u);
+      if (q < ab_end) {
+        const uint2 r = rng[q];
+        ent.x = r.x;
+        ent.y = r.y;
+        if (L == 1) {
+          ent.z = (u32)ypat[q];
+          ent.w = (u32)(ypat[q] >> 32);
+        }
+        nc = (r.y - r.x + 31u) >> 5;
+        if (nc > (u32)kListChunks) nc = 0;
+      }
+      u32 incl = nc;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const u32 up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += up;
+      }
+      const u32 at = base + incl - nc;
+      for (u32 j = 0; j < nc; ++j) {
+        clist[at + j] = ent;
+        ent.x += 32u;
+      }
+      base += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    // pad to a whole number of unrolled iterations with chunks past every bucket end
+    const u32 padded = (base + (u32)kChunkUnroll - 1u) / (u32)kChunkUnroll * (u32)kChunkUnroll;
+    if ((u32)lane < padded - base) clist[base + lane] = make_uint4(0u, 0u, (u32)g_begin, 0u);  // empty: first == end
+    if (lane == 0) s_nchunks = (int)padded;
+  }
+  __syncthreads();
+
+  u32 *queue = queues + warp * kQueue;
+  u32 qn = 0;
+  // (1) the flat chunk list: kChunkUnroll independent chunks per warp and iteration
+  {
+    const u64 *__restrict__ keysB = gv.keys[0];
+    const int nchunks = s_nchunks;
+    for (int c0 = warp * kChunkUnroll; c0 < nchunks; c0 += kScanWarps * kChunkUnroll) {
+      Onv<L> k[kChunkUnroll], y[kChunkUnroll];
+      u32 pos[kChunkUnroll];
+      bool valid[kChunkUnroll];
+#pragma unroll
+      for (int u = 0; u < kChunkUnroll; ++u) {
+        const uint4 ent = clist[c0 + u];  // nchunks is a multiple of kChunkUnroll
+        pos[u] = ent.x + (u32)lane;
+        valid[u] = pos[u] < ent.y;
+        if (L == 1) {
+          y[u].w[0] = (u64)ent.z | ((u64)ent.w << 32);
+        } else {
+#pragma unroll
+          for (int w = 0; w < L; ++w) y[u].w[w] = ypat[ent.z * L + w];
+        }
+#pragma unroll
+        for (int w = 0; w < L; ++w) k[u].w[w] = ~y[u].w[w];  // past the bucket end: a key at distance 64 L
+        if (valid[u]) k[u] = load_onv<L>(keysB + (size_t)pos[u] * L);
+      }
+#pragma unroll
+      for (int u = 0; u < kChunkUnroll; ++u) push_hits(queue, qn, key_distance<L>(k[u], y[u], kOdd) == 2u, pos[u]);
+    }
+  }
+  // (2) the two own groups and the alpha-beta groups that are not in the list: one warp per group
+  for (int q = g_begin + warp; q < g_end; q += kScanWarps) {
+    const uint2 r = rng[q];
+    const u32 size = r.y - r.x;
+    if (size == 0) continue;
+    if (q < sB) {  // alpha-beta doubles on top of beta single q
+      if (size <= 32u * (u32)kListChunks) continue;  // done in (1)
+      Onv<L> y;
+#pragma unroll
+      for (int w = 0; w < L; ++w) y.w[w] = ypat[q * L + w];
+      if (size > big_ab) qn = search_bucket<L>(gv.keys[0], r.x, r.y, y, msk, &s_sg[0], 0u, queue, qn, nullptr);
+      else scan_bucket<L>(gv.keys[0], r.x, r.y, y, kOdd, 1u << 2, 0u, queue, qn, nullptr);
+    } else if (q == sB) {  // own beta string: x itself, alpha singles, alpha-alpha doubles
+      if (size > 16u * (u32)(g.sA + g.noAA * g.nvAA + 1)) qn = search_bucket<L>(gv.keys[0], r.x, r.y, x, msk, &s_sg[1], 0u, queue, qn, self_pos + s);
+      else scan_bucket<L>(gv.keys[0], r.x, r.y, x, kOdd, (1u << 2) | (1u << 4), 0u, queue, qn, self_pos + s);
+    } else {  // own alpha string: beta singles, beta-beta doubles
+      if (size > 16u * (u32)(sB + g.noBB * g.nvBB)) qn = search_bucket<L>(gv.keys[1], r.x, r.y, x, msk, &s_sg[2], 0x80000000u, queue, qn, nullptr);
+      else scan_bucket<L>(gv.keys[1], r.x, r.y, x, kEven, (1u << 2) | (1u << 4), 0x80000000u, queue, qn, nullptr);
+    }
+  }
+
+  // publish this warp's hits (no CTA barrier: every warp owns its run record)
+  __syncwarp();
+  u32 off = 0;
+  bool over = qn > (u32)kQueue;
+  if (lane == 0 && !over && qn) {
+    off = atomicAdd(cursor, qn);
+    if (off > hit_cap || qn > hit_cap - off) over = true;  // buffer exhausted
+  }
+  off = __shfl_sync(0xffffffffu, off, 0);
+  over = __shfl_sync(0xffffffffu, (int)over, 0) != 0;
+  if (lane == 0) {
+    const HitRun run = {off, over ? kOverflow : qn};
+    *my_run = run;
+  }
+  if (!over)
+    for (u32 e = lane; e < qn; e += 32) hits[off + e] = queue[e];
+}
+
+// ---- evaluation ---------------------------------------------------------------------------------------------
+template <int L, bool CPLX>
+__global__ void __launch_bounds__(kEvalThreads)
+eloc_eval_kernel(const u64 *__restrict__ bra, long long n, const double *__restrict__ h1e, const double *__restrict__ h2e,
+                 const u64 *__restrict__ key, const double *__restrict__ psi, long long N, GroupView gv,
+                 const HitRun *__restrict__ runs, const u32 *__restrict__ hits, const u32 *__restrict__ self_pos,
+                 const double *__restrict__ hii, double *__restrict__ eloc, double *__restrict__ psi0_out, int splits, ExcGeom g) {
+  __shared__ OrbLists s_lists[kEvalThreads / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long s = (long long)blockIdx.x * (kEvalThreads / 32) + warp;
+  if (s >= n) return;
+  const Onv<L> x = load_onv<L>(bra + s * L);
+  const int nruns = splits * kScanWarps;
+  const HitRun *my_runs = runs + s * nruns;
+  bool redo = false;
+  for (int w = lane; w < nruns; w += 32) redo |= (my_runs[w].cnt & kOverflow) != 0;
+  redo = __any_sync(0xffffffffu, redo);
+
+  Cplx p0 = {0.0, 0.0}, acc = {0.0, 0.0};
+  if (redo) {
+    // the reference's route: every excitation in row order, classic binary search in the sorted table
+    OrbLists &lists = s_lists[warp];
+    build_lists<L>(x, g.sorb, g.noA, g.noB, lists, lane);
+    __syncwarp();
+    const long long id0 = classic_search<L>(key, N, x);
+    if (id0 >= 0) p0 = load_psi<CPLX>(psi, id0);
+    if (lane == 0) accumulate<CPLX>(acc, p0, p0, hii[s]);
+    for (int r = lane; r < g.nsd; r += 32) {
+      const Exc e = decode_exc(g, lists, r);
+      const long long id = classic_search<L>(key, N, apply_exc<L>(x, e));
+      if (id >= 0) accumulate<CPLX>(acc, load_psi<CPLX>(psi, id), p0, exc_element<L, double>(x, e, h1e, h2e, g.sorb));
+    }
+  } else {
+    const u32 sp = self_pos[s];
+    if (sp != kNoSelf) p0 = load_psi<CPLX>(psi, (long long)__ldg(gv.rows[0] + sp));
+    if (lane == 0) accumulate<CPLX>(acc, p0, p0, hii[s]);  // row 0: (psi0/psi0) * H_xx
+    for (int w = 0; w < nruns; ++w) {
+      const HitRun run = my_runs[w];
+      for (u32 e = lane; e < run.cnt; e += 32) {
+        const u32 h = hits[run.off + e];
+        const int grouping = (int)(h >> 31);
+        const u32 pos = h & 0x7fffffffu;
+        const Onv<L> y = load_onv<L>((grouping ? gv.keys[1] : gv.keys[0]) + (size_t)pos * L);
+        const long long id = (long long)__ldg((grouping ? gv.rows[1] : gv.rows[0]) + pos);
+        accumulate<CPLX>(acc, load_psi<CPLX>(psi, id), p0, rederived_element<L, double>(x, y, h1e, h2e, g.sorb, g.nele));
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    acc.re += __shfl_xor_sync(0xffffffffu, acc.re, o);
+    if (CPLX) acc.im += __shfl_xor_sync(0xffffffffu, acc.im, o);
+  }
+  if (lane == 0) {
+    if (CPLX) {
+      eloc[2 * s] = acc.re;
+      eloc[2 * s + 1] = acc.im;
+      psi0_out[2 * s] = p0.re;
+      psi0_out[2 * s + 1] = p0.im;
+    } else {
+      eloc[s] = acc.re;
+      psi0_out[s] = p0.re;
+    }
+  }
+}
+
+// ---- host side --------------------------------------------------------------------------------------------
+// splits: CTAs per sample -- more than one only when there are too few samples to fill the GPU
+static int scan_splits(long long n, int n_groups) {
+  if (n <= 0) return 1;
+  long long want = (148LL * 8 + n - 1) / n;
+  const long long cap = n_groups / kScanWarps > 1 ? n_groups / kScanWarps : 1;
+  if (want > cap) want = cap;
+  return (int)(want < 1 ? 1 : want);
+}
+
+struct ElocScratch {
+  long long hii, self_pos, runs, cursor, hits, total;
+  long long hit_cap, batch;
+  int splits;  // same for every batch of the call (sized for the first, largest one)
+};
+
+static ElocScratch eloc_scratch_layout(long long n, const ExcGeom &g) {
+  ElocScratch l;
+  // hits per sample the global buffer can take before samples fall back to the full route, and a
+  // batch size that keeps the buffer at about 1 GiB
+  long long per_sample = (long long)g.nsd / 4;
+  per_sample = per_sample < 256 ? 256 : (per_sample > 4096 ? 4096 : per_sample);
+  l.batch = (1LL << 28) / per_sample;
+  l.batch = l.batch < 1024 ? 1024 : (l.batch > (1LL << 18) ? (1LL << 18) : l.batch);
+  const long long nb = n < l.batch ? n : l.batch;
+  l.splits = scan_splits(nb, g.noB * g.nvB + 2);
+  l.hii = 0;
+  l.self_pos = (l.hii + 8 * n + 15) / 16 * 16;
+  l.runs = (l.self_pos + 4 * nb + 15) / 16 * 16;
+  l.cursor = l.runs + (long long)sizeof(HitRun) * nb * l.splits * kScanWarps;
+  l.hits = l.cursor + 256;
+  l.hit_cap = nb * per_sample + 65536;
+  if (l.hit_cap > 0x7fffffffLL) l.hit_cap = 0x7fffffffLL;
+  l.total = l.hits + 4 * l.hit_cap + 256;
+  return l;
+}
+
+long long eloc_scratch_bytes(long long n, const ExcGeom &g) { return eloc_scratch_layout(n, g).total; }
+
+int launch_diag_f64(const u64 *bra, const double *h1e, const double *h2e, double *out, long long n, long long stride, int L,
+                    int sorb, int nele, cudaStream_t st);
+
+template <int L, bool CPLX>
+static int launch_eloc_LC(const u64 *bra, long long n, const double *h1e, const double *h2e, const u64 *key, const double *psi,
+                          long long N, const GroupView &gv, char *scratch, const ElocScratch &lay, double *eloc, double *psi0,
+                          const ExcGeom &g, cudaStream_t st) {
+  double *hii = reinterpret_cast<double *>(scratch + lay.hii);
+  u32 *self_pos = reinterpret_cast<u32 *>(scratch + lay.self_pos);
+  HitRun *runs = reinterpret_cast<HitRun *>(scratch + lay.runs);
+  u32 *cursor = reinterpret_cast<u32 *>(scratch + lay.cursor);
+  u32 *hits = reinterpret_cast<u32 *>(scratch + lay.hits);
+  const size_t smem = scan_queue_offset(g) + sizeof(u32) * kQueue * kScanWarps;
+  if (smem > 48 * 1024 &&
+      cudaFuncSetAttribute(eloc_scan_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    return check_launch("eloc_scan_kernel smem opt-in");
+  const int w = CPLX ? 2 : 1;
+  for (long long b0 = 0; b0 < n; b0 += lay.batch) {
+    const long long nb = n - b0 < lay.batch ? n - b0 : lay.batch;
+    const int splits = lay.splits;
+    if (cudaMemsetAsync(cursor, 0, 4, st) != cudaSuccess) return check_launch("eloc cursor memset");
+    if (cudaMemsetAsync(self_pos, 0xff, 4 * (size_t)nb, st) != cudaSuccess) return check_launch("eloc self memset");
+    eloc_scan_kernel<L><<<(unsigned)(nb * splits), kScanThreads, smem, st>>>(bra + b0 * L, nb, gv, runs, hits, self_pos, cursor,
+                                                                              (u32)lay.hit_cap, splits, g);
+    count_launch();
+    if (int rc = check_launch("eloc_scan_kernel")) return rc;
+    const unsigned eb = (unsigned)((nb + kEvalThreads / 32 - 1) / (kEvalThreads / 32));
+    eloc_eval_kernel<L, CPLX><<<eb, kEvalThreads, 0, st>>>(bra + b0 * L, nb, h1e, h2e, key, psi, N, gv, runs, hits, self_pos,
+                                                            hii + b0, eloc + b0 * w, psi0 + b0 * w, splits, g);
+    count_launch();
+    if (int rc = check_launch("eloc_eval_kernel")) return rc;
+  }
+  return 0;
+}
+
+int launch_eloc(const u64 *bra, long long n, const double *h1e, const double *h2e, const u64 *key, const double *psi, int cplx,
+                long long N, const void *group_ws, void *scratch, long long scratch_bytes, double *eloc, double *psi0,
+                const ExcGeom &g, cudaStream_t st) {
+  if (n == 0) return 0;
+  const ElocScratch lay = eloc_scratch_layout(n, g);
+  if (scratch_bytes < lay.total) {
+    set_error("eloc scratch too small: %lld < %lld bytes", scratch_bytes, lay.total);
+    return 4;
+  }
+  char *sc = static_cast<char *>(scratch);
+  if (int rc = launch_diag_f64(bra, h1e, h2e, reinterpret_cast<double *>(sc + lay.hii), n, 1, g.L, g.sorb, g.nele, st)) return rc;
+  const GroupView gv = group_view(group_ws, N, g.L);
+#define PYNQS_ELOC_CASE(LL)                                                                                                  \
+  case LL:                                                                                                                   \
+    return cplx ? launch_eloc_LC<LL, true>(bra, n, h1e, h2e, key, psi, N, gv, sc, lay, eloc, psi0, g, st)                    \
+                : launch_eloc_LC<LL, false>(bra, n, h1e, h2e, key, psi, N, gv, sc, lay, eloc, psi0, g, st);
+  switch (g.L) {
+    PYNQS_ELOC_CASE(1)
+    PYNQS_ELOC_CASE(2)
+    PYNQS_ELOC_CASE(3)
+  }
+#undef PYNQS_ELOC_CASE
+  set_error("unsupported ONV length L=%d", g.L);
+  return 1;
+}
+
+}  // namespace pynqs

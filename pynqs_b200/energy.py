@@ -21,7 +21,7 @@ from .lut import WavefunctionLUT
 def local_energy_sample_space(x: Tensor, h1e: Tensor, h2e: Tensor, WF_LUT: WavefunctionLUT, sorb: int, nele: int,
                               noa: int, nob: int, dtype=torch.double) -> Tuple[Tensor, Tensor, Tensor]:
     """Returns (eloc, sloc, psi_x) like _only_sample_space (eloc.py:508); sloc is zero (no spin-raising)."""
-    eloc, psi0 = ops.eloc_sample_space(x, h1e, h2e, sorb, nele, noa, nob, WF_LUT.bra_key, WF_LUT.wf_value, WF_LUT.hash_index)
+    eloc, psi0 = ops.eloc_sample_space(x, h1e, h2e, sorb, nele, noa, nob, WF_LUT.bra_key, WF_LUT.wf_value, WF_LUT.group_index)
     return eloc.to(dtype), torch.zeros_like(eloc).to(dtype), psi0.to(dtype)
 
 

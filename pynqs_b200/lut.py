@@ -88,11 +88,10 @@ class WavefunctionLUT:
         self.rank_idx = [0] + split_length_idx(bra_key.size(0), world_size)
         self.rank_begin = self.rank_idx[rank]
         self.rank_end = self.rank_idx[rank + 1]
+        # device accelerators, built on first use: the hash index behind lookup(), the string-grouped
+        # copies behind the one-pass local energy
         self._hash = None
-        if self._bra_key.is_cuda:
-            from .C_extension import HashIndex
-
-            self._hash = HashIndex(self._bra_key)
+        self._group = None
 
     @property
     def idx_sorted(self) -> Tensor:
@@ -117,11 +116,23 @@ class WavefunctionLUT:
 
     @property
     def hash_index(self):
+        if self._hash is None and self._bra_key.is_cuda:
+            from .C_extension import HashIndex
+
+            self._hash = HashIndex(self._bra_key)
         return self._hash
 
     @property
+    def group_index(self):
+        if self._group is None and self._bra_key.is_cuda:
+            from .C_extension import GroupIndex
+
+            self._group = GroupIndex(self._bra_key)
+        return self._group
+
+    @property
     def memory(self) -> float:
-        extra = self._hash.nbytes if self._hash is not None else 0
+        extra = sum(ix.nbytes for ix in (self._hash, self._group) if ix is not None)
         return (self.bra_key.numel() + extra) / 2**20
 
     def lookup(self, onv: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
@@ -129,7 +140,7 @@ class WavefunctionLUT:
         -- public_function.py:817-838."""
         from .C_extension import wavefunction_lut
 
-        idx_array, mask = wavefunction_lut(self._bra_key, onv, self.sorb, hash_index=self._hash)
+        idx_array, mask = wavefunction_lut(self._bra_key, onv, self.sorb, hash_index=self.hash_index)
         baseline = torch.arange(onv.size(0), device=onv.device, dtype=torch.int64)
         onv_idx = baseline[mask]
         onv_not_idx = baseline[torch.logical_not(mask)]
@@ -145,7 +156,7 @@ class WavefunctionLUT:
 
     def clean_memory(self) -> None:
         del self._bra_key, self._wf_value
-        self._hash = None
+        self._hash = self._group = None
 
     def __repr__(self) -> str:
         return (

@@ -242,10 +242,10 @@ def test_eloc_sample_missing_from_table_gives_nan_like_reference():
     assert (psi_x[10:] == 0).all()
 
 
-def test_eloc_dense_table_overflows_the_candidate_queues():
-    """Full 24-spin-orbital space (6a6b, 853 776 keys): EVERY connected determinant is in the table, so
-    the per-warp candidate queues of the filter kernel overflow and the eval kernel redoes the rows in
-    full -- the result must still equal the oracle and the three-call path."""
+def test_eloc_dense_table_full_space():
+    """Full 24-spin-orbital space (6a6b, 853 776 keys): EVERY connected determinant is in the table
+    (1819 hits per sample) and the groups are large enough (924 keys) for the alpha-beta groups to be
+    searched instead of scanned -- the result must equal the oracle and the three-call path."""
     sorb, noA, noB, nele = 24, 6, 6, 12
     import itertools
 
@@ -273,6 +273,57 @@ def test_eloc_dense_table_overflows_the_candidate_queues():
     assert bool(mask.all())
 
 
+def test_eloc_hit_queue_overflow_takes_the_full_route():
+    """Fe2S2 shape with ALL 15504 alpha strings on three beta strings: the own-beta group of a sample
+    yields 75 + 1050 hits in one warp (> 512 queue slots), so the sample is redone by full enumeration
+    + classic search -- same numbers as the oracle."""
+    import itertools
+
+    sorb, noA, noB, nele = 40, 15, 15, 30
+    a = np.array([sum(1 << (2 * k) for k in c) for c in itertools.combinations(range(20), 15)], dtype=np.uint64)
+    b = np.array([sum(1 << (2 * k + 1) for k in c) for c in (range(15), list(range(14)) + [17], list(range(13)) + [15, 19])], dtype=np.uint64)
+    keys = (a[:, None] | b[None, :]).reshape(-1).view(np.uint8).reshape(-1, 8)
+    keys = keys[np.random.default_rng(3).permutation(keys.shape[0])]
+    psi = S.random_psi(keys.shape[0], seed=4)
+    h1e, h2e = S.random_packed_integrals(sorb, seed=7, symmetric=True)
+    lut = WavefunctionLUT(dev(keys), dev(psi), sorb, DEV, rank=0, world_size=1)
+    x = keys[:40]
+    e1, _, p1 = local_energy_sample_space(dev(x), dev(h1e), dev(h2e), lut, sorb, nele, noA, noB)
+    order = O.sort_onv(keys)
+    want = O.eloc_sample_space(x[:5], h1e, h2e, keys[order], psi[order], sorb, nele, noA, noB)
+    np.testing.assert_allclose(e1[:5].cpu().numpy(), want, rtol=1e-12, atol=0)
+    e3, _, p3 = local_energy_three_call(dev(x), dev(h1e), dev(h2e), lut, sorb, nele, noA, noB, batch=8)
+    np.testing.assert_allclose(e1.cpu().numpy(), e3.cpu().numpy(), rtol=1e-12, atol=0)
+    assert torch.equal(p1, p3)
+
+
+@pytest.mark.parametrize("alpha_only", [True, False])
+def test_eloc_one_huge_group_is_searched(alpha_only):
+    """36 spin orbitals, 9 electrons of ONE spin: the whole table (all 48 620 strings) is a single group,
+    35x larger than the 1378 determinants connected to a sample -> the own-string bucket is searched
+    (binary search inside the bucket) instead of scanned."""
+    import itertools
+
+    sorb = 36
+    noA, noB = (9, 0) if alpha_only else (0, 9)
+    shift = 0 if alpha_only else 1
+    keys64 = np.array([sum(1 << (2 * k + shift) for k in c) for c in itertools.combinations(range(18), 9)], dtype=np.uint64)
+    keys = keys64.view(np.uint8).reshape(-1, 8)
+    keys = keys[np.random.default_rng(9).permutation(keys.shape[0])]
+    psi = S.random_psi(keys.shape[0], seed=10, complex_=alpha_only)
+    h1e, h2e = S.random_packed_integrals(sorb, seed=11, symmetric=True)
+    lut = WavefunctionLUT(dev(keys), dev(psi), sorb, DEV, rank=0, world_size=1)
+    x = keys[:64]
+    dtype = torch.complex128 if alpha_only else torch.double
+    e1, _, p1 = local_energy_sample_space(dev(x), dev(h1e), dev(h2e), lut, sorb, 9, noA, noB, dtype)
+    order = O.sort_onv(keys)
+    want = O.eloc_sample_space(x[:8], h1e, h2e, keys[order], psi[order], sorb, 9, noA, noB)
+    np.testing.assert_allclose(e1[:8].cpu().numpy(), want, rtol=1e-12, atol=0)
+    e3, _, p3 = local_energy_three_call(dev(x), dev(h1e), dev(h2e), lut, sorb, 9, noA, noB, dtype, batch=32)
+    np.testing.assert_allclose(e1.cpu().numpy(), e3.cpu().numpy(), rtol=1e-12, atol=0)
+    assert torch.equal(p1, p3)
+
+
 def test_eloc_multiword_onvs_against_oracle():
     """L = 2 (100 spin orbitals) and L = 3 (132): one-pass E_loc vs the oracle on a small table."""
     for sorb, noA, noB, nkeys in ((100, 3, 3, 4000), (132, 3, 2, 3000)):
@@ -294,7 +345,7 @@ def test_eloc_multiword_onvs_against_oracle():
 
 
 def test_eloc_h50_shape_many_splits():
-    """Config-4 geometry: 100 spin orbitals, 25a25b, M = 571 876 (70 splits per sample, L = 2)."""
+    """Config-4 geometry: 100 spin orbitals, 25a25b, M = 571 876, 627 groups per sample split over many CTAs (L = 2)."""
     sorb, noA, noB = 100, 25, 25
     seeds = S.random_onvs(2, sorb, noA, noB, seed=44)
     comb = O.comb(seeds, sorb, noA, noB).reshape(-1, 16)
