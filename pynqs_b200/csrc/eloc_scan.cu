@@ -26,6 +26,8 @@
 // table -- the same set binary_search_BigInteger would find.  Tables with duplicate keys, and
 // samples whose hits overflow the queues, take the reference's route instead (enumerate every
 // excitation, classic binary search); no floating point atomics anywhere.
+#include <cstdlib>
+
 #include "gindex.cuh"
 #include "lut.cuh"
 #include "rederive.cuh"
@@ -166,6 +168,20 @@ __device__ __forceinline__ void scan_bucket(const u64 *__restrict__ keys, u32 s,
 //   kind 0: alpha-beta doubles on top of a beta single, base = x with that single applied (targets: sA alpha singles)
 //   kind 1: own beta string  (targets: x itself, sA alpha singles, noAA * nvAA alpha-alpha doubles)
 //   kind 2: own alpha string (targets: sB beta singles, noBB * nvBB beta-beta doubles)
+// walk the folded strings [s, e) of one bucket (HALF route): distance of each to `pat`, allowed distances in `allow`
+__device__ __forceinline__ u32 scan_half(const u32 *__restrict__ half, u32 s, u32 e, u32 pat, u32 allow, u32 flags, u32 *queue, u32 qn) {
+  const u32 lane = threadIdx.x & 31;
+  for (u32 k0 = s; k0 < e; k0 += 64) {
+    const u32 p0 = k0 + lane, p1 = p0 + 32;
+    u32 d0 = 31u, d1 = 31u;
+    if (p0 < e) d0 = (u32)__popc(__ldg(half + p0) ^ pat);
+    if (p1 < e) d1 = (u32)__popc(__ldg(half + p1) ^ pat);
+    push_hits(queue, qn, ((allow >> min(d0, 31u)) & 1u) != 0u, p0 | flags);
+    push_hits(queue, qn, ((allow >> min(d1, 31u)) & 1u) != 0u, p1 | flags);
+  }
+  return qn;
+}
+
 struct SearchGeom {  // per kind: number of single targets, hole pairs, particle pairs and their table offsets
   int nS, nH, nP, oS, oH, oP, self, pad;
 };
@@ -201,42 +217,64 @@ __device__ __noinline__ u32 search_bucket(const u64 *__restrict__ keys, u32 s, u
   return qn;
 }
 
-// dynamic shared memory of the scan kernel: lists | patterns | tables | buckets | chunk list | queues
-constexpr int kListChunksDecl = 4;
-__host__ __device__ inline size_t scan_queue_offset(const ExcGeom &g) {
+// dynamic shared memory of the scan kernel:
+//   lists | patterns [nG][L] | tables (search route) | buckets [nG] | duplicate filter | long groups | chunk list | queues
+constexpr int kListChunks = 4;     // groups of up to kListChunks * 32 keys go to the flat chunk list
+constexpr int kChunkUnroll = 4;    // independent key loads in flight per lane (full keys)
+constexpr int kHalfUnroll = 8;     // ... (folded 32-bit strings)
+constexpr int kDupWords = 512;     // 16384-bit filter for "two of my groups share a bucket"
+
+struct ScanSmem {
+  size_t ypat, msk, rng, dup, lgrp, clist, queues, total;
+};
+__host__ __device__ inline ScanSmem scan_smem(const ExcGeom &g) {
   const size_t sB = (size_t)g.noB * g.nvB, nG = sB + 2;
-  size_t o = sizeof(OrbLists) + 8 * nG * g.L + 8 * (size_t)table_offsets(g).total + 8 * nG;
-  o = ((o + 15) & ~(size_t)15) + 16 * (sB * kListChunksDecl + 8);
-  return (o + 15) & ~(size_t)15;
+  ScanSmem m;
+  size_t o = (sizeof(OrbLists) + 15) & ~(size_t)15;
+  m.ypat = o;
+  o += 8 * nG * g.L;
+  m.msk = o;
+  o += 8 * (size_t)table_offsets(g).total;
+  m.rng = o;
+  o += 8 * nG;
+  m.dup = o;
+  o += 4 * kDupWords;
+  m.lgrp = o;
+  o = (o + 2 * (sB + 2) + 15) & ~(size_t)15;
+  m.clist = o;
+  o += 16 * (sB * kListChunks + 8);
+  m.queues = o;
+  m.total = o + sizeof(u32) * kQueue * kScanWarps;
+  return m;
 }
 
-// groups of at most kListChunks * 32 keys are cut into 32-key chunks and all chunks of a sample are
-// processed as one flat, evenly divided list (a warp would otherwise idle on its small groups while
-// another one walks a large group); larger groups are walked (or searched) by one warp each.
-constexpr int kListChunks = kListChunksDecl;
-constexpr int kChunkUnroll = 4;  // independent key loads in flight per lane
+// hit word: position in the grouped copy | kHitA (alpha-grouped copy) | kHitOwn (found in the scan of one of
+// the sample's own strings, HALF route only -- the eval kernel checks the class of the key accordingly)
+constexpr u32 kHitA = 0x80000000u, kHitOwn = 0x40000000u, kHitPos = 0x3fffffffu;
 
-template <int L>
+// Small groups are cut into 32-key chunks and all chunks of a sample are processed as one flat, evenly
+// divided list (a warp would otherwise idle on its small groups while another one walks a large group);
+// larger groups are walked (or searched) by one warp each.
+// HALF (L = 1, N < 2^30): the test reads the folded 32-bit strings; a key that passes may sit in the bucket
+// by hash collision, which the eval kernel detects on the full key.
+template <int L, bool HALF>
 __global__ void __launch_bounds__(kScanThreads)
 eloc_scan_kernel(const u64 *__restrict__ bra, long long n, GroupView gv, HitRun *__restrict__ runs, u32 *__restrict__ hits,
                  u32 *__restrict__ self_pos, u32 *cursor, u32 hit_cap, int splits, ExcGeom g) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const TableOffsets to = table_offsets(g);
+  const ScanSmem sm = scan_smem(g);
   const int sB = g.noB * g.nvB, nG = sB + 2;
   OrbLists &lists = *reinterpret_cast<OrbLists *>(smem_raw);
-  u64 *ypat = reinterpret_cast<u64 *>(smem_raw + sizeof(OrbLists));  // [nG][L] pattern of every group
-  u64 *msk = ypat + (size_t)nG * L;                                   // excitation tables (search route only)
-  uint2 *rng = reinterpret_cast<uint2 *>(msk + to.total);             // [nG] bucket of every group
-  // chunk list: {first key, bucket end, pattern (L = 1) or group (L > 1)} -- one 16-byte load per chunk
-  uint4 *clist = reinterpret_cast<uint4 *>(smem_raw + scan_queue_offset(g)) - ((size_t)sB * kListChunks + 8);
-  u32 *queues = reinterpret_cast<u32 *>(smem_raw + scan_queue_offset(g));
-  __shared__ int s_nchunks;
+  u64 *ypat = reinterpret_cast<u64 *>(smem_raw + sm.ypat);  // [nG][L] pattern of every group
+  u64 *msk = reinterpret_cast<u64 *>(smem_raw + sm.msk);    // excitation tables (search route only)
+  uint2 *rng = reinterpret_cast<uint2 *>(smem_raw + sm.rng);  // [nG] bucket of every group
+  u32 *dupf = reinterpret_cast<u32 *>(smem_raw + sm.dup);
+  unsigned short *lgrp = reinterpret_cast<unsigned short *>(smem_raw + sm.lgrp);  // groups walked by one warp each
+  uint4 *clist4 = reinterpret_cast<uint4 *>(smem_raw + sm.clist);  // {first key, bucket end, pattern | group}
+  uint2 *clist2 = reinterpret_cast<uint2 *>(smem_raw + sm.clist);  // HALF: {first key, bucket end}
+  u32 *queues = reinterpret_cast<u32 *>(smem_raw + sm.queues);
+  __shared__ int s_nchunks, s_nlong;
   __shared__ SearchGeom s_sg[3];
-  if (threadIdx.x == 0) {
-    s_sg[0] = SearchGeom{g.sA, 0, 0, to.sa, 0, 0, 0, 0};
-    s_sg[1] = SearchGeom{g.sA, g.noAA, g.nvAA, to.sa, to.hpa, to.ppa, 1, 0};
-    s_sg[2] = SearchGeom{sB, g.noBB, g.nvBB, to.sb, to.hpb, to.ppb, 0, 0};
-  }
 
   const long long s = splits == 1 ? (long long)blockIdx.x : (long long)(blockIdx.x / (unsigned)splits);
   const int split = splits == 1 ? 0 : (int)(blockIdx.x - (unsigned)s * (unsigned)splits);
@@ -252,14 +290,21 @@ eloc_scan_kernel(const u64 *__restrict__ bra, long long n, GroupView gv, HitRun 
   }
   const Onv<L> x = load_onv<L>(bra + s * L);
   if (threadIdx.x < 32) build_lists<L>(x, g.sorb, g.noA, g.noB, lists, threadIdx.x);
+  if (HALF) {
+    for (int t = threadIdx.x; t < kDupWords; t += kScanThreads) dupf[t] = 0u;
+  }
   __syncthreads();
 
-  // the groups of this slice: pattern and bucket of each
+  // ---- the groups of this slice: pattern and bucket of each ---------------------------------------------------
   const int per = (nG + splits - 1) / splits;
   const int g_begin = split * per, g_end = min(nG, g_begin + per), ab_end = min(g_end, sB);
   const u32 big_ab = 16u * (u32)g.sA;  // an alpha-beta group this large is searched, not walked
-  bool need_tables = false;
-  for (int q = g_begin + (int)threadIdx.x; q < g_end; q += kScanThreads) {
+  const u32 big_own_b = 16u * (u32)(g.sA + g.noAA * g.nvAA + 1), big_own_a = 16u * (u32)(sB + g.noBB * g.nvBB);
+  bool need_tables = false, maybe_dup = false;
+  uint2 my_r = make_uint2(0u, 0u);
+  int my_q = -1;
+  // (HALF: the buckets of ALL groups, so that every slice agrees on which group walks a shared bucket)
+  for (int q = (HALF ? 0 : g_begin) + (int)threadIdx.x; q < (HALF ? nG : g_end); q += kScanThreads) {
     Onv<L> y = x;
     if (q < sB) {  // beta single q: hole = q % noB, particle = q / noB of the merged beta list
       const u32 pb = fdiv((u32)q, g.by_noB), hb = (u32)q - pb * g.noB;
@@ -267,25 +312,48 @@ eloc_scan_kernel(const u64 *__restrict__ bra, long long n, GroupView gv, HitRun 
       flip_bit<L>(y, lists.b[g.noB + pb] & 0xff);
     }
     const int grouping = q == sB + 1 ? 1 : 0;
-    const u32 *st = (grouping ? gv.start[1] : gv.start[0]) + group_bucket<L>(y, grouping, gv.shift);  // no dynamic index into the param struct
+    const u32 bkt = group_bucket<L>(y, grouping, gv.shift);
+    const u32 *st = (grouping ? gv.start[1] : gv.start[0]) + bkt;  // no dynamic index into the param struct
     const uint2 r = make_uint2(__ldg(st), __ldg(st + 1));
     rng[q] = r;
 #pragma unroll
     for (int w = 0; w < L; ++w) ypat[q * L + w] = y.w[w];
     const u32 size = r.y - r.x;
     if (q < sB) need_tables |= size > big_ab;
-    else if (q == sB) need_tables |= size > 16u * (u32)(g.sA + g.noAA * g.nvAA + 1);
-    else need_tables |= size > 16u * (u32)(sB + g.noBB * g.nvBB);
+    else if (q == sB) need_tables |= size > big_own_b;
+    else need_tables |= size > big_own_a;
+    if (HALF && q < sB && size && size <= big_ab) {  // the folded test cannot tell two beta strings in one bucket
+      my_r = r;  // apart: a bucket must be WALKED for only one of the groups that map to it (searches are exact
+      my_q = q;  // per group and stay).  L = 1: at most 256 alpha-beta groups, one per thread.
+      const u32 bit = 1u << (bkt & 31u);
+      maybe_dup = (atomicOr(&dupf[(bkt >> 5) & (kDupWords - 1)], bit) & bit) != 0u;
+    }
   }
   need_tables = __syncthreads_or((int)need_tables) != 0;
-  if (need_tables) {
-    for_each_table_entry(g, lists, to, [&](int t, int, u32 e0, u32 e1) { msk[t] = msk_make<L>(e0 & 0xffu, e1 & 0xffu); });
+  if (HALF && maybe_dup) {  // rare: filter collision or two groups in one bucket -- keep the lowest group only
+    for (int p = 0; p < sB; ++p) {
+      if (p == my_q) continue;
+      const uint2 rp = rng[p];  // non-empty buckets are equal iff their ranges are
+      if (rp.x == my_r.x && rp.y == my_r.y) rng[max(p, my_q)] = make_uint2(0u, 0u);
+    }
   }
-  if (warp == 0) {  // chunk list of the small alpha-beta groups, in group order
-    u32 base = 0;
+  if (need_tables) {
+    const TableOffsets to = table_offsets(g);
+    for_each_table_entry(g, lists, to, [&](int t, int, u32 e0, u32 e1) { msk[t] = msk_make<L>(e0 & 0xffu, e1 & 0xffu); });
+    if (threadIdx.x == 0) {
+      s_sg[0] = SearchGeom{g.sA, 0, 0, to.sa, 0, 0, 0, 0};
+      s_sg[1] = SearchGeom{g.sA, g.noAA, g.nvAA, to.sa, to.hpa, to.ppa, 1, 0};
+      s_sg[2] = SearchGeom{sB, g.noBB, g.nvBB, to.sb, to.hpb, to.ppb, 0, 0};
+    }
+  }
+  if (HALF) __syncthreads();  // the duplicate pass may have emptied buckets
+  constexpr int UN = HALF ? kHalfUnroll : kChunkUnroll;
+  if (warp == 0) {  // chunk list of the small alpha-beta groups, in group order; the others go to the long list
+    u32 base = 0, nlong = 0;
     for (int q0 = g_begin; q0 < ab_end; q0 += 32) {
       const int q = q0 + lane;
       u32 nc = 0;
+      bool is_long = false;
       uint4 ent = make_uint4(0u, 0u, (u32)q, 0u);
       if (q < ab_end) {
         const uint2 r = rng[q];
@@ -296,7 +364,8 @@ eloc_scan_kernel(const u64 *__restrict__ bra, long long n, GroupView gv, HitRun 
           ent.w = (u32)(ypat[q] >> 32);
         }
         nc = (r.y - r.x + 31u) >> 5;
-        if (nc > (u32)kListChunks) nc = 0;
+        is_long = nc > (u32)kListChunks;
+        if (is_long) nc = 0;
       }
       u32 incl = nc;
 #pragma unroll
@@ -306,33 +375,58 @@ eloc_scan_kernel(const u64 *__restrict__ bra, long long n, GroupView gv, HitRun 
       }
       const u32 at = base + incl - nc;
       for (u32 j = 0; j < nc; ++j) {
-        clist[at + j] = ent;
+        if (HALF) clist2[at + j] = make_uint2(ent.x, ent.y);
+        else clist4[at + j] = ent;
         ent.x += 32u;
       }
       base += __shfl_sync(0xffffffffu, incl, 31);
+      const u32 lm = __ballot_sync(0xffffffffu, is_long);
+      if (is_long) lgrp[nlong + (u32)__popc(lm & ((1u << lane) - 1u))] = (unsigned short)q;
+      nlong += (u32)__popc(lm);
     }
-    // pad to a whole number of unrolled iterations with chunks past every bucket end
-    const u32 padded = (base + (u32)kChunkUnroll - 1u) / (u32)kChunkUnroll * (u32)kChunkUnroll;
-    if ((u32)lane < padded - base) clist[base + lane] = make_uint4(0u, 0u, (u32)g_begin, 0u);  // empty: first == end
+    // the own groups of this slice are walked by one warp each, too
+    if (lane == 0) {
+      for (int q = max(g_begin, sB); q < g_end; ++q) lgrp[nlong++] = (unsigned short)q;
+      s_nlong = (int)nlong;
+    }
+    // pad to a whole number of unrolled iterations with empty chunks (first == end)
+    const u32 padded = (base + (u32)UN - 1u) / (u32)UN * (u32)UN;
+    if ((u32)lane < padded - base) {
+      if (HALF) clist2[base + lane] = make_uint2(0u, 0u);
+      else clist4[base + lane] = make_uint4(0u, 0u, (u32)g_begin, 0u);
+    }
     if (lane == 0) s_nchunks = (int)padded;
   }
   __syncthreads();
 
   u32 *queue = queues + warp * kQueue;
   u32 qn = 0;
-  // (1) the flat chunk list: kChunkUnroll independent chunks per warp and iteration
-  {
-    const u64 *__restrict__ keysB = gv.keys[0];
-    const int nchunks = s_nchunks;
-    for (int c0 = warp * kChunkUnroll; c0 < nchunks; c0 += kScanWarps * kChunkUnroll) {
-      Onv<L> k[kChunkUnroll], y[kChunkUnroll];
-      u32 pos[kChunkUnroll];
-      bool valid[kChunkUnroll];
+  // ---- (1) the flat chunk list: UN independent chunks per warp and iteration ---------------------------------------
+  const int nchunks = s_nchunks;
+  if (HALF) {
+    const u32 *__restrict__ halfB = gv.half[0];
+    const u32 ax = fold_alpha(x.w[0]);
+    for (int c0 = warp * UN; c0 < nchunks; c0 += kScanWarps * UN) {
+      u32 h[UN], pos[UN];
 #pragma unroll
-      for (int u = 0; u < kChunkUnroll; ++u) {
-        const uint4 ent = clist[c0 + u];  // nchunks is a multiple of kChunkUnroll
+      for (int u = 0; u < UN; ++u) {
+        const uint2 ent = clist2[c0 + u];
         pos[u] = ent.x + (u32)lane;
-        valid[u] = pos[u] < ent.y;
+        h[u] = ~ax;  // past the bucket end: distance 32
+        if (pos[u] < ent.y) h[u] = __ldg(halfB + pos[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < UN; ++u) push_hits(queue, qn, __popc(h[u] ^ ax) == 2, pos[u]);
+    }
+  } else {
+    const u64 *__restrict__ keysB = gv.keys[0];
+    for (int c0 = warp * UN; c0 < nchunks; c0 += kScanWarps * UN) {
+      Onv<L> k[UN], y[UN];
+      u32 pos[UN];
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+        const uint4 ent = clist4[c0 + u];
+        pos[u] = ent.x + (u32)lane;
         if (L == 1) {
           y[u].w[0] = (u64)ent.z | ((u64)ent.w << 32);
         } else {
@@ -341,30 +435,49 @@ eloc_scan_kernel(const u64 *__restrict__ bra, long long n, GroupView gv, HitRun 
         }
 #pragma unroll
         for (int w = 0; w < L; ++w) k[u].w[w] = ~y[u].w[w];  // past the bucket end: a key at distance 64 L
-        if (valid[u]) k[u] = load_onv<L>(keysB + (size_t)pos[u] * L);
+        if (pos[u] < ent.y) k[u] = load_onv<L>(keysB + (size_t)pos[u] * L);
       }
 #pragma unroll
-      for (int u = 0; u < kChunkUnroll; ++u) push_hits(queue, qn, key_distance<L>(k[u], y[u], kOdd) == 2u, pos[u]);
+      for (int u = 0; u < UN; ++u) push_hits(queue, qn, key_distance<L>(k[u], y[u], kOdd) == 2u, pos[u]);
     }
   }
-  // (2) the two own groups and the alpha-beta groups that are not in the list: one warp per group
-  for (int q = g_begin + warp; q < g_end; q += kScanWarps) {
+  // ---- (2) the own groups and the long alpha-beta groups: one warp per group ---------------------------------------
+  const int nlong = s_nlong;
+  for (int i = warp; i < nlong; i += kScanWarps) {
+    const int q = lgrp[i];
     const uint2 r = rng[q];
     const u32 size = r.y - r.x;
     if (size == 0) continue;
-    if (q < sB) {  // alpha-beta doubles on top of beta single q
-      if (size <= 32u * (u32)kListChunks) continue;  // done in (1)
-      Onv<L> y;
+    Onv<L> y;
 #pragma unroll
-      for (int w = 0; w < L; ++w) y.w[w] = ypat[q * L + w];
+    for (int w = 0; w < L; ++w) y.w[w] = ypat[q * L + w];
+    if (q < sB) {  // alpha-beta doubles on top of beta single q
       if (size > big_ab) qn = search_bucket<L>(gv.keys[0], r.x, r.y, y, msk, &s_sg[0], 0u, queue, qn, nullptr);
+      else if (HALF) qn = scan_half(gv.half[0], r.x, r.y, fold_alpha(x.w[0]), 1u << 2, 0u, queue, qn);
       else scan_bucket<L>(gv.keys[0], r.x, r.y, y, kOdd, 1u << 2, 0u, queue, qn, nullptr);
     } else if (q == sB) {  // own beta string: x itself, alpha singles, alpha-alpha doubles
-      if (size > 16u * (u32)(g.sA + g.noAA * g.nvAA + 1)) qn = search_bucket<L>(gv.keys[0], r.x, r.y, x, msk, &s_sg[1], 0u, queue, qn, self_pos + s);
-      else scan_bucket<L>(gv.keys[0], r.x, r.y, x, kOdd, (1u << 2) | (1u << 4), 0u, queue, qn, self_pos + s);
+      if (size > big_own_b) {
+        qn = search_bucket<L>(gv.keys[0], r.x, r.y, x, msk, &s_sg[1], HALF ? kHitOwn : 0u, queue, qn, self_pos + s);
+      } else if (HALF) {
+        const u32 ax = fold_alpha(x.w[0]);
+        for (u32 k0 = r.x; k0 < r.y; k0 += 32) {
+          const u32 pos = k0 + (u32)lane;
+          u32 d = 31u;
+          if (pos < r.y) d = (u32)__popc(__ldg(gv.half[0] + pos) ^ ax);
+          if (d == 0u && gv.keys[0][pos] == x.w[0]) self_pos[s] = pos;  // the sample itself (checked on the full key)
+          push_hits(queue, qn, d == 2u || d == 4u, pos | kHitOwn);
+        }
+      } else {
+        scan_bucket<L>(gv.keys[0], r.x, r.y, x, kOdd, (1u << 2) | (1u << 4), 0u, queue, qn, self_pos + s);
+      }
     } else {  // own alpha string: beta singles, beta-beta doubles
-      if (size > 16u * (u32)(sB + g.noBB * g.nvBB)) qn = search_bucket<L>(gv.keys[1], r.x, r.y, x, msk, &s_sg[2], 0x80000000u, queue, qn, nullptr);
-      else scan_bucket<L>(gv.keys[1], r.x, r.y, x, kEven, (1u << 2) | (1u << 4), 0x80000000u, queue, qn, nullptr);
+      if (size > big_own_a) {
+        qn = search_bucket<L>(gv.keys[1], r.x, r.y, x, msk, &s_sg[2], kHitA | (HALF ? kHitOwn : 0u), queue, qn, nullptr);
+      } else if (HALF) {
+        qn = scan_half(gv.half[1], r.x, r.y, fold_beta(x.w[0]), (1u << 2) | (1u << 4), kHitA | kHitOwn, queue, qn);
+      } else {
+        scan_bucket<L>(gv.keys[1], r.x, r.y, x, kEven, (1u << 2) | (1u << 4), kHitA, queue, qn, nullptr);
+      }
     }
   }
 
@@ -387,7 +500,7 @@ eloc_scan_kernel(const u64 *__restrict__ bra, long long n, GroupView gv, HitRun 
 }
 
 // ---- evaluation ---------------------------------------------------------------------------------------------
-template <int L, bool CPLX>
+template <int L, bool CPLX, bool HALF>
 __global__ void __launch_bounds__(kEvalThreads)
 eloc_eval_kernel(const u64 *__restrict__ bra, long long n, const double *__restrict__ h1e, const double *__restrict__ h2e,
                  const u64 *__restrict__ key, const double *__restrict__ psi, long long N, GroupView gv,
@@ -426,9 +539,18 @@ eloc_eval_kernel(const u64 *__restrict__ bra, long long n, const double *__restr
       const HitRun run = my_runs[w];
       for (u32 e = lane; e < run.cnt; e += 32) {
         const u32 h = hits[run.off + e];
-        const int grouping = (int)(h >> 31);
-        const u32 pos = h & 0x7fffffffu;
+        const bool grouping = (h & kHitA) != 0u;
+        const u32 pos = HALF ? (h & kHitPos) : (h & ~kHitA);
         const Onv<L> y = load_onv<L>((grouping ? gv.keys[1] : gv.keys[0]) + (size_t)pos * L);
+        if (HALF) {  // the scan tested one folded string only: class of the full key vs the scan it came from
+          const u64 d = y.w[0] ^ x.w[0];
+          const int na = __popcll(d & kEven), nb = __popcll(d & kOdd);
+          bool ok;
+          if (!(h & kHitOwn)) ok = na == 2 && nb == 2;               // alpha-beta double (bucket of a beta single)
+          else if (!grouping) ok = nb == 0 && (na == 2 || na == 4);  // own beta string
+          else ok = na == 0 && (nb == 2 || nb == 4);                 // own alpha string
+          if (!ok) continue;
+        }
         const long long id = (long long)__ldg((grouping ? gv.rows[1] : gv.rows[0]) + pos);
         accumulate<CPLX>(acc, load_psi<CPLX>(psi, id), p0, rederived_element<L, double>(x, y, h1e, h2e, g.sorb, g.nele));
       }
@@ -494,7 +616,7 @@ long long eloc_scratch_bytes(long long n, const ExcGeom &g) { return eloc_scratc
 int launch_diag_f64(const u64 *bra, const double *h1e, const double *h2e, double *out, long long n, long long stride, int L,
                     int sorb, int nele, cudaStream_t st);
 
-template <int L, bool CPLX>
+template <int L, bool CPLX, bool HALF>
 static int launch_eloc_LC(const u64 *bra, long long n, const double *h1e, const double *h2e, const u64 *key, const double *psi,
                           long long N, const GroupView &gv, char *scratch, const ElocScratch &lay, double *eloc, double *psi0,
                           const ExcGeom &g, cudaStream_t st) {
@@ -503,9 +625,9 @@ static int launch_eloc_LC(const u64 *bra, long long n, const double *h1e, const 
   HitRun *runs = reinterpret_cast<HitRun *>(scratch + lay.runs);
   u32 *cursor = reinterpret_cast<u32 *>(scratch + lay.cursor);
   u32 *hits = reinterpret_cast<u32 *>(scratch + lay.hits);
-  const size_t smem = scan_queue_offset(g) + sizeof(u32) * kQueue * kScanWarps;
+  const size_t smem = scan_smem(g).total;
   if (smem > 48 * 1024 &&
-      cudaFuncSetAttribute(eloc_scan_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+      cudaFuncSetAttribute(eloc_scan_kernel<L, HALF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return check_launch("eloc_scan_kernel smem opt-in");
   const int w = CPLX ? 2 : 1;
   for (long long b0 = 0; b0 < n; b0 += lay.batch) {
@@ -513,12 +635,12 @@ static int launch_eloc_LC(const u64 *bra, long long n, const double *h1e, const 
     const int splits = lay.splits;
     if (cudaMemsetAsync(cursor, 0, 4, st) != cudaSuccess) return check_launch("eloc cursor memset");
     if (cudaMemsetAsync(self_pos, 0xff, 4 * (size_t)nb, st) != cudaSuccess) return check_launch("eloc self memset");
-    eloc_scan_kernel<L><<<(unsigned)(nb * splits), kScanThreads, smem, st>>>(bra + b0 * L, nb, gv, runs, hits, self_pos, cursor,
+    eloc_scan_kernel<L, HALF><<<(unsigned)(nb * splits), kScanThreads, smem, st>>>(bra + b0 * L, nb, gv, runs, hits, self_pos, cursor,
                                                                               (u32)lay.hit_cap, splits, g);
     count_launch();
     if (int rc = check_launch("eloc_scan_kernel")) return rc;
     const unsigned eb = (unsigned)((nb + kEvalThreads / 32 - 1) / (kEvalThreads / 32));
-    eloc_eval_kernel<L, CPLX><<<eb, kEvalThreads, 0, st>>>(bra + b0 * L, nb, h1e, h2e, key, psi, N, gv, runs, hits, self_pos,
+    eloc_eval_kernel<L, CPLX, HALF><<<eb, kEvalThreads, 0, st>>>(bra + b0 * L, nb, h1e, h2e, key, psi, N, gv, runs, hits, self_pos,
                                                             hii + b0, eloc + b0 * w, psi0 + b0 * w, splits, g);
     count_launch();
     if (int rc = check_launch("eloc_eval_kernel")) return rc;
@@ -540,8 +662,15 @@ int launch_eloc(const u64 *bra, long long n, const double *h1e, const double *h2
   const GroupView gv = group_view(group_ws, N, g.L);
 #define PYNQS_ELOC_CASE(LL)                                                                                                  \
   case LL:                                                                                                                   \
-    return cplx ? launch_eloc_LC<LL, true>(bra, n, h1e, h2e, key, psi, N, gv, sc, lay, eloc, psi0, g, st)                    \
-                : launch_eloc_LC<LL, false>(bra, n, h1e, h2e, key, psi, N, gv, sc, lay, eloc, psi0, g, st);
+    return cplx ? launch_eloc_LC<LL, true, false>(bra, n, h1e, h2e, key, psi, N, gv, sc, lay, eloc, psi0, g, st)             \
+                : launch_eloc_LC<LL, false, false>(bra, n, h1e, h2e, key, psi, N, gv, sc, lay, eloc, psi0, g, st);
+  // folded 32-bit strings: one-word ONVs, two flag bits in the hit word.  PYNQS_FULL_KEYS=1 forces the
+  // full-key route (the one multi-word ONVs take) -- used by the parity tests to cover both.
+  const char *full = getenv("PYNQS_FULL_KEYS");
+  if (g.L == 1 && N < (1LL << 30) && !(full && full[0] == '1')) {
+    return cplx ? launch_eloc_LC<1, true, true>(bra, n, h1e, h2e, key, psi, N, gv, sc, lay, eloc, psi0, g, st)
+                : launch_eloc_LC<1, false, true>(bra, n, h1e, h2e, key, psi, N, gv, sc, lay, eloc, psi0, g, st);
+  }
   switch (g.L) {
     PYNQS_ELOC_CASE(1)
     PYNQS_ELOC_CASE(2)

@@ -29,6 +29,10 @@ GroupLayout group_layout(long long N, int L) {
     l.rows_off[g] = o;
     o = up(o + N * 4);
   }
+  for (int g = 0; g < 2; ++g) {
+    l.half_off[g] = o;
+    if (L == 1) o = up(o + N * 4);
+  }
   l.scratch_off = o;
   for (int g = 0; g < 2; ++g)
     for (int k = 0; k < 2; ++k) {
@@ -57,6 +61,7 @@ GroupView group_view(const void *ws, long long N, int L) {
     v.start[g] = reinterpret_cast<const u32 *>(b + l.start_off[g]);
     v.keys[g] = reinterpret_cast<const u64 *>(b + l.keys_off[g]);
     v.rows[g] = reinterpret_cast<const u32 *>(b + l.rows_off[g]);
+    v.half[g] = L == 1 ? reinterpret_cast<const u32 *>(b + l.half_off[g]) : nullptr;
   }
   v.shift = 32u - l.log2_buckets;
   return v;
@@ -85,7 +90,8 @@ template <int L>
 __global__ void __launch_bounds__(256)
 group_finish_kernel(const u64 *__restrict__ key, long long N, u32 log2_buckets, const u32 *__restrict__ bktB,
                     const u32 *__restrict__ bktA, const u32 *__restrict__ rowsB, const u32 *__restrict__ rowsA, u64 *__restrict__ keysB,
-                    u64 *__restrict__ keysA, u32 *__restrict__ startB, u32 *__restrict__ startA) {
+                    u64 *__restrict__ keysA, u32 *__restrict__ startB, u32 *__restrict__ startA, u32 *__restrict__ halfB,
+                    u32 *__restrict__ halfA) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
   const bool ga = blockIdx.y != 0;
@@ -96,6 +102,11 @@ group_finish_kernel(const u64 *__restrict__ key, long long N, u32 log2_buckets, 
   const u32 row = rows[i];
 #pragma unroll
   for (int w = 0; w < L; ++w) keys[i * L + w] = key[(long long)row * L + w];
+  if (L == 1) {  // the other string of the key, folded
+    const u64 k0 = key[(long long)row * L];
+    if (ga) halfA[i] = fold_beta(k0);
+    else halfB[i] = fold_alpha(k0);
+  }
   // bucket boundaries: start[t] = first position whose bucket id is >= t
   const u32 b = bkt[i];
   const long long first = i == 0 ? 0 : (long long)bkt[i - 1] + 1;
@@ -138,6 +149,7 @@ int launch_group_build(const u64 *key, long long N, int L, void *ws, long long w
   u32 *bkt[2][2] = {{reinterpret_cast<u32 *>(b + l.bkt_off[0][0]), reinterpret_cast<u32 *>(b + l.bkt_off[0][1])},
                     {reinterpret_cast<u32 *>(b + l.bkt_off[1][0]), reinterpret_cast<u32 *>(b + l.bkt_off[1][1])}};
   u32 *iota = reinterpret_cast<u32 *>(b + l.iota_off);
+  u32 *half[2] = {reinterpret_cast<u32 *>(b + l.half_off[0]), reinterpret_cast<u32 *>(b + l.half_off[1])};
   if (cudaMemsetAsync(hdr, 0, sizeof(GroupHeader), st) != cudaSuccess) return check_launch("group header memset");
   if (N == 0) {
     group_empty_kernel<<<148, 256, 0, st>>>(hdr, l.log2_buckets, start[0], start[1]);
@@ -165,7 +177,7 @@ int launch_group_build(const u64 *key, long long N, int L, void *ws, long long w
   const dim3 grid(blocks, 2);
 #define PYNQS_FINISH(LL)                                                                                                           \
   group_finish_kernel<LL><<<grid, 256, 0, st>>>(key, N, l.log2_buckets, bkt[0][1], bkt[1][1], rows[0], rows[1], keys[0], keys[1], \
-                                                start[0], start[1])
+                                                start[0], start[1], half[0], half[1])
   switch (L) {
     case 1: PYNQS_FINISH(1); break;
     case 2: PYNQS_FINISH(2); break;

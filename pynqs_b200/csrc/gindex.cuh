@@ -14,6 +14,10 @@
 // group with XOR + popcount.  A group is a handful of consecutive keys: coalesced loads, no hashing
 // of the connected determinants, and what survives the test IS a hit (row known, nothing to verify).
 //
+// For one-word ONVs (sorb <= 64) each copy also carries the OTHER string of every key folded into
+// 32 bits (fold_alpha / fold_beta: injective and popcount-preserving), so that the test of a key
+// is one 4-byte load, one XOR and one popcount; what passes is checked against the full key later.
+//
 // Layout: the table is copied twice, bucketed by hash(beta string) ("B") and by hash(alpha string)
 // ("A"): start_g[2^b + 1] (u32), keys_g[N] (the keys in bucket order; inside a bucket ascending,
 // because the sort is stable and the input table is sorted), rows_g[N] (row in the sorted table).
@@ -34,7 +38,7 @@ static_assert(sizeof(GroupHeader) == 256, "header is 256 bytes");
 
 struct GroupLayout {
   u32 log2_buckets;
-  long long start_off[2], keys_off[2], rows_off[2], scratch_off, total;
+  long long start_off[2], keys_off[2], rows_off[2], half_off[2], scratch_off, total;
   long long bkt_off[2][2], iota_off;  // build scratch: bucket ids (in / out per grouping), identity rows
   long long cub_off;
   size_t cub_bytes;
@@ -51,8 +55,19 @@ struct GroupView {
   const u32 *start[2];  // [0] bucketed by beta string, [1] by alpha string
   const u64 *keys[2];
   const u32 *rows[2];
+  const u32 *half[2];  // L = 1 only: [0] folded alpha strings in B order, [1] folded beta strings in A order
   u32 shift;  // 32 - log2_buckets
 };
+
+// the alpha (even) / beta (odd) bits of a one-word ONV folded into 32 bits
+__device__ __forceinline__ u32 fold_alpha(u64 w) {
+  const u64 e = w & kEven;
+  return (u32)e | ((u32)(e >> 32) << 1);
+}
+__device__ __forceinline__ u32 fold_beta(u64 w) {
+  const u64 o = w & kOdd;
+  return ((u32)o >> 1) | (u32)(o >> 32);
+}
 
 // 32-bit hash of one spin string (the words masked to the even or the odd bits)
 template <int L>

@@ -197,8 +197,19 @@ def test_empty_and_tiny_inputs():
 
 
 # ---- E_loc ------------------------------------------------------------------------------------------
+@pytest.fixture(params=["folded", "full_keys"])
+def scan_route(request, monkeypatch):
+    """One-word ONVs are scanned through folded 32-bit strings; PYNQS_FULL_KEYS=1 forces the full-key
+    route that multi-word ONVs (and tables of 2^30 keys or more) take.  Both must give the same numbers."""
+    if request.param == "full_keys":
+        monkeypatch.setenv("PYNQS_FULL_KEYS", "1")
+    else:
+        monkeypatch.delenv("PYNQS_FULL_KEYS", raising=False)
+    return request.param
+
+
 @pytest.mark.parametrize("tag,cplx", [("real", False), ("complex", True)])
-def test_eloc_matches_reference_python(tag, cplx):
+def test_eloc_matches_reference_python(tag, cplx, scan_route):
     f = fe2s2()
     g = load(f"eloc_fe2s2_{tag}")
     psi = S.random_psi(f["ci"].shape[0], seed=int(g["psi_seed"]), complex_=cplx)
@@ -216,7 +227,7 @@ def test_eloc_matches_reference_python(tag, cplx):
     np.testing.assert_array_equal(psi3.cpu().numpy(), g["psi_x"])
 
 
-def test_eloc_full_space_and_rayleigh_quotient():
+def test_eloc_full_space_and_rayleigh_quotient(scan_route):
     g = load("eloc_c1_fullspace")
     keys = S.random_onvs(400, 12, 3, 3, seed=51)
     h1e, h2e = S.random_packed_integrals(12, seed=52, symmetric=True)
@@ -242,7 +253,7 @@ def test_eloc_sample_missing_from_table_gives_nan_like_reference():
     assert (psi_x[10:] == 0).all()
 
 
-def test_eloc_dense_table_full_space():
+def test_eloc_dense_table_full_space(scan_route):
     """Full 24-spin-orbital space (6a6b, 853 776 keys): EVERY connected determinant is in the table
     (1819 hits per sample) and the groups are large enough (924 keys) for the alpha-beta groups to be
     searched instead of scanned -- the result must equal the oracle and the three-call path."""
@@ -273,7 +284,7 @@ def test_eloc_dense_table_full_space():
     assert bool(mask.all())
 
 
-def test_eloc_hit_queue_overflow_takes_the_full_route():
+def test_eloc_hit_queue_overflow_takes_the_full_route(scan_route):
     """Fe2S2 shape with ALL 15504 alpha strings on three beta strings: the own-beta group of a sample
     yields 75 + 1050 hits in one warp (> 512 queue slots), so the sample is redone by full enumeration
     + classic search -- same numbers as the oracle."""
@@ -298,7 +309,7 @@ def test_eloc_hit_queue_overflow_takes_the_full_route():
 
 
 @pytest.mark.parametrize("alpha_only", [True, False])
-def test_eloc_one_huge_group_is_searched(alpha_only):
+def test_eloc_one_huge_group_is_searched(alpha_only, scan_route):
     """36 spin orbitals, 9 electrons of ONE spin: the whole table (all 48 620 strings) is a single group,
     35x larger than the 1378 determinants connected to a sample -> the own-string bucket is searched
     (binary search inside the bucket) instead of scanned."""
@@ -322,6 +333,26 @@ def test_eloc_one_huge_group_is_searched(alpha_only):
     e3, _, p3 = local_energy_three_call(dev(x), dev(h1e), dev(h2e), lut, sorb, 9, noA, noB, dtype, batch=32)
     np.testing.assert_allclose(e1.cpu().numpy(), e3.cpu().numpy(), rtol=1e-12, atol=0)
     assert torch.equal(p1, p3)
+
+
+@pytest.mark.parametrize("nkeys", [40, 300, 3000])
+def test_eloc_tiny_tables_many_groups_per_bucket(nkeys, scan_route):
+    """Fe2S2 shape on tables of a few dozen to a few thousand keys: far fewer buckets than the 77 groups
+    of a sample need, so groups of one sample share buckets (every bucket must still be walked once
+    per sample) and unrelated strings share buckets with them (must be rejected on the full key)."""
+    sorb, noA, noB = 40, 15, 15
+    seeds = S.random_onvs(4, sorb, noA, noB, seed=91)
+    comb = O.comb(seeds, sorb, noA, noB).reshape(-1, 8)
+    rng = np.random.default_rng(92)
+    keys = np.unique(np.concatenate([seeds, comb[rng.permutation(comb.shape[0])[: nkeys - 4]]]), axis=0)
+    psi = S.random_psi(keys.shape[0], seed=93)
+    h1e, h2e = S.random_packed_integrals(sorb, seed=7, symmetric=True)
+    lut = WavefunctionLUT(dev(keys), dev(psi), sorb, DEV, rank=0, world_size=1)
+    x = np.concatenate([seeds, keys[:12]])
+    e1, _, p1 = local_energy_sample_space(dev(x), dev(h1e), dev(h2e), lut, sorb, noA + noB, noA, noB)
+    order = O.sort_onv(keys)
+    want = O.eloc_sample_space(x, h1e, h2e, keys[order], psi[order], sorb, noA + noB, noA, noB)
+    np.testing.assert_allclose(e1.cpu().numpy(), want, rtol=1e-12, atol=0)
 
 
 def test_eloc_multiword_onvs_against_oracle():
@@ -361,7 +392,7 @@ def test_eloc_h50_shape_many_splits():
 
 
 # ---- larger, size-independent properties ---------------------------------------------------------------
-def test_fe2s2_shape_at_scale_properties():
+def test_fe2s2_shape_at_scale_properties(scan_route):
     """Config-2 geometry (40 sorb, 15a15b, M = 7876) at 2e5 table keys / 8192 evaluated samples:
     fused == rederived, hash lookup == classic search, one-pass E_loc == three-call path,
     mean energy within 1e-10 Ha; oracle spot check."""
