@@ -1,0 +1,40 @@
+#!/usr/bin/env python
+"""Instruction / stall-sample share of each phase of a kernel (phases = code between barriers, calls and exits),
+from an .ncu-rep captured with --import-source on:  python profiles/sass_phases.py rep [samples_per_launch] [lo hi]
+With lo hi: per-instruction listing (executions per sample) of SASS lines lo..hi."""
+import csv
+import subprocess
+import sys
+
+
+def main(path, per=1, lo=None, hi=None):
+    out = subprocess.run(["ncu", "-i", path, "--page", "source", "--csv"], capture_output=True, text=True).stdout.splitlines()
+    rows = list(csv.reader(out))
+    hdr = next(r for r in rows if "Instructions Executed" in r)
+    hi_ = rows.index(hdr)
+    ie, src, smp = hdr.index("Instructions Executed"), hdr.index("Source"), hdr.index("# Samples")
+    body = [r for r in rows[hi_ + 1:] if len(r) == len(hdr)]
+    T = sum(int(r[ie]) for r in body)
+    S = sum(int(r[smp]) for r in body)
+    print(f"total warp-instructions {T} ({T / per:.0f} per unit), stall samples {S}, SASS lines {len(body)}")
+    if lo is not None:
+        for i in range(lo, hi + 1):
+            r = body[i]
+            print(f"{i:5d} {int(r[ie]) / per:8.1f} {int(r[smp]):6d}  {r[src].strip()[:90]}")
+        return
+    acc = accs = 0
+    start = 0
+    for i, r in enumerate(body):
+        acc += int(r[ie])
+        accs += int(r[smp])
+        t = r[src]
+        if "BAR.SYNC" in t or "CALL" in t or "EXIT" in t or "RET" in t or i == len(body) - 1:
+            if acc > T * 0.003:
+                print(f"[{start:5d},{i:5d}] {100 * acc / T:5.1f}% inst ({acc / per:7.0f}/unit) {100 * accs / max(S, 1):5.1f}% samples   ends: {t.strip()[:50]}")
+            acc = accs = 0
+            start = i + 1
+
+
+if __name__ == "__main__":
+    a = sys.argv
+    main(a[1], float(a[2]) if len(a) > 2 else 1, int(a[3]) if len(a) > 4 else None, int(a[4]) if len(a) > 4 else None)

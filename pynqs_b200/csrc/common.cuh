@@ -156,8 +156,8 @@ struct OrbLists {
 // One warp builds both lists: lane handles orbitals lane, lane+32, ...  The bra word itself is
 // the occupancy ballot; ranks come from popcounts of masked words.
 template <int L>
-__device__ __forceinline__ void build_lists(const Onv<L> &x, int sorb, int noA, int noB, OrbLists &out, int lane) {
-  for (int k = lane; k < sorb; k += 32) {
+__device__ __forceinline__ void build_lists(const Onv<L> &x, int sorb, int noA, int noB, OrbLists &out, int lane, int stride = 32) {
+  for (int k = lane; k < sorb; k += stride) {
     const bool occ = test_bit<L>(x, k);
     const u64 spin = (k & 1) ? kOdd : kEven;
     int occ_same = 0, occ_all = 0, below_same = 0;

@@ -225,26 +225,26 @@ constexpr int kHalfUnroll = 8;     // ... (folded 32-bit strings)
 constexpr int kDupWords = 512;     // 16384-bit filter for "two of my groups share a bucket"
 
 struct ScanSmem {
-  size_t ypat, msk, rng, dup, lgrp, clist, queues, total;
+  u32 ypat, msk, rng, dup, lgrp, clist, queues, total;
 };
 __host__ __device__ inline ScanSmem scan_smem(const ExcGeom &g) {
   const size_t sB = (size_t)g.noB * g.nvB, nG = sB + 2;
   ScanSmem m;
   size_t o = (sizeof(OrbLists) + 15) & ~(size_t)15;
-  m.ypat = o;
+  m.ypat = (u32)o;
   o += 8 * nG * g.L;
-  m.msk = o;
+  m.msk = (u32)o;
   o += 8 * (size_t)table_offsets(g).total;
-  m.rng = o;
+  m.rng = (u32)o;
   o += 8 * nG;
-  m.dup = o;
+  m.dup = (u32)o;
   o += 4 * kDupWords;
-  m.lgrp = o;
+  m.lgrp = (u32)o;
   o = (o + 2 * (sB + 2) + 15) & ~(size_t)15;
-  m.clist = o;
+  m.clist = (u32)o;
   o += 16 * (sB * kListChunks + 8);
-  m.queues = o;
-  m.total = o + sizeof(u32) * kQueue * kScanWarps;
+  m.queues = (u32)o;
+  m.total = (u32)(o + sizeof(u32) * kQueue * kScanWarps);
   return m;
 }
 
@@ -260,9 +260,8 @@ constexpr u32 kHitA = 0x80000000u, kHitOwn = 0x40000000u, kHitPos = 0x3fffffffu;
 template <int L, bool HALF>
 __global__ void __launch_bounds__(kScanThreads)
 eloc_scan_kernel(const u64 *__restrict__ bra, long long n, GroupView gv, HitRun *__restrict__ runs, u32 *__restrict__ hits,
-                 u32 *__restrict__ self_pos, u32 *cursor, u32 hit_cap, int splits, ExcGeom g) {
+                 u32 *__restrict__ self_pos, u32 *cursor, u32 hit_cap, int splits, ExcGeom g, ScanSmem sm) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const ScanSmem sm = scan_smem(g);
   const int sB = g.noB * g.nvB, nG = sB + 2;
   OrbLists &lists = *reinterpret_cast<OrbLists *>(smem_raw);
   u64 *ypat = reinterpret_cast<u64 *>(smem_raw + sm.ypat);  // [nG][L] pattern of every group
@@ -274,6 +273,8 @@ eloc_scan_kernel(const u64 *__restrict__ bra, long long n, GroupView gv, HitRun 
   uint2 *clist2 = reinterpret_cast<uint2 *>(smem_raw + sm.clist);  // HALF: {first key, bucket end}
   u32 *queues = reinterpret_cast<u32 *>(smem_raw + sm.queues);
   __shared__ int s_nchunks, s_nlong;
+  __shared__ u32 s_flags;
+  __shared__ u32 wtot[kScanWarps * 10];  // work per (round of 256 groups, warp); nG <= 2306 -> 10 rounds
   __shared__ SearchGeom s_sg[3];
 
   const long long s = splits == 1 ? (long long)blockIdx.x : (long long)(blockIdx.x / (unsigned)splits);
@@ -289,10 +290,11 @@ eloc_scan_kernel(const u64 *__restrict__ bra, long long n, GroupView gv, HitRun 
     return;
   }
   const Onv<L> x = load_onv<L>(bra + s * L);
-  if (threadIdx.x < 32) build_lists<L>(x, g.sorb, g.noA, g.noB, lists, threadIdx.x);
+  if (threadIdx.x < 64) build_lists<L>(x, g.sorb, g.noA, g.noB, lists, threadIdx.x, 64);
   if (HALF) {
     for (int t = threadIdx.x; t < kDupWords; t += kScanThreads) dupf[t] = 0u;
   }
+  if (threadIdx.x == 0) s_flags = 0u;
   __syncthreads();
 
   // ---- the groups of this slice: pattern and bucket of each ---------------------------------------------------
@@ -300,44 +302,76 @@ eloc_scan_kernel(const u64 *__restrict__ bra, long long n, GroupView gv, HitRun 
   const int g_begin = split * per, g_end = min(nG, g_begin + per), ab_end = min(g_end, sB);
   const u32 big_ab = 16u * (u32)g.sA;  // an alpha-beta group this large is searched, not walked
   const u32 big_own_b = 16u * (u32)(g.sA + g.noAA * g.nvAA + 1), big_own_a = 16u * (u32)(sB + g.noBB * g.nvBB);
-  bool need_tables = false, maybe_dup = false;
+  // (HALF: the buckets of ALL groups, so that every slice agrees on which group walks a shared bucket)
+  const int q_lo = HALF ? 0 : g_begin, q_hi = HALF ? nG : g_end;
+  constexpr int UN = HALF ? kHalfUnroll : kChunkUnroll;
+  // what a group adds to the two work lists: chunks (low half) and one-warp-per-group entries (high half)
+  auto work_of = [&](int q, uint2 r) -> u32 {
+    if (q < g_begin || q >= g_end || r.y == r.x) return 0u;
+    if (q >= sB) return 1u << 16;
+    const u32 nc = (r.y - r.x + 31u) >> 5;
+    return nc > (u32)kListChunks ? (1u << 16) : nc;
+  };
+  auto warp_scan = [&](u32 v) -> u32 {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const u32 up = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= o) v += up;
+    }
+    return v;
+  };
+  bool maybe_dup = false;
   uint2 my_r = make_uint2(0u, 0u);
   int my_q = -1;
-  // (HALF: the buckets of ALL groups, so that every slice agrees on which group walks a shared bucket)
-  for (int q = (HALF ? 0 : g_begin) + (int)threadIdx.x; q < (HALF ? nG : g_end); q += kScanThreads) {
-    Onv<L> y = x;
-    if (q < sB) {  // beta single q: hole = q % noB, particle = q / noB of the merged beta list
-      const u32 pb = fdiv((u32)q, g.by_noB), hb = (u32)q - pb * g.noB;
-      flip_bit<L>(y, lists.b[hb] & 0xff);
-      flip_bit<L>(y, lists.b[g.noB + pb] & 0xff);
-    }
-    const int grouping = q == sB + 1 ? 1 : 0;
-    const u32 bkt = group_bucket<L>(y, grouping, gv.shift);
-    const u32 *st = (grouping ? gv.start[1] : gv.start[0]) + bkt;  // no dynamic index into the param struct
-    const uint2 r = make_uint2(__ldg(st), __ldg(st + 1));
-    rng[q] = r;
+  for (int q0 = q_lo; q0 < q_hi; q0 += kScanThreads) {
+    const int q = q0 + (int)threadIdx.x;
+    uint2 r = make_uint2(0u, 0u);
+    if (q < q_hi) {
+      Onv<L> y = x;
+      if (q < sB) {  // beta single q: hole = q % noB, particle = q / noB of the merged beta list
+        const u32 pb = fdiv((u32)q, g.by_noB), hb = (u32)q - pb * g.noB;
+        flip_bit<L>(y, lists.b[hb] & 0xff);
+        flip_bit<L>(y, lists.b[g.noB + pb] & 0xff);
+      }
+      const int grouping = q == sB + 1 ? 1 : 0;
+      const u32 bkt = group_bucket<L>(y, grouping, gv.shift);
+      const u32 *st = (grouping ? gv.start[1] : gv.start[0]) + bkt;  // no dynamic index into the param struct
+      r = make_uint2(__ldg(st), __ldg(st + 1));
+      rng[q] = r;
 #pragma unroll
-    for (int w = 0; w < L; ++w) ypat[q * L + w] = y.w[w];
-    const u32 size = r.y - r.x;
-    if (q < sB) need_tables |= size > big_ab;
-    else if (q == sB) need_tables |= size > big_own_b;
-    else need_tables |= size > big_own_a;
-    if (HALF && q < sB && size && size <= big_ab) {  // the folded test cannot tell two beta strings in one bucket
-      my_r = r;  // apart: a bucket must be WALKED for only one of the groups that map to it (searches are exact
-      my_q = q;  // per group and stay).  L = 1: at most 256 alpha-beta groups, one per thread.
-      const u32 bit = 1u << (bkt & 31u);
-      maybe_dup = (atomicOr(&dupf[(bkt >> 5) & (kDupWords - 1)], bit) & bit) != 0u;
+      for (int w = 0; w < L; ++w) ypat[q * L + w] = y.w[w];
+      const u32 size = r.y - r.x;
+      if (size > (q < sB ? big_ab : (q == sB ? big_own_b : big_own_a))) atomicOr(&s_flags, 1u);  // searched: needs the tables
+      if (HALF && q < sB && size && size <= big_ab) {  // the folded test cannot tell two beta strings in one bucket
+        my_r = r;  // apart: a bucket must be WALKED for only one of the groups that map to it (searches are exact
+        my_q = q;  // per group and stay).  L = 1: at most 256 alpha-beta groups, one per thread.
+        const u32 bit = 1u << (bkt & 31u);
+        maybe_dup = (atomicOr(&dupf[(bkt >> 5) & (kDupWords - 1)], bit) & bit) != 0u;
+        if (maybe_dup) atomicOr(&s_flags, 2u);
+      }
     }
+    const u32 tot = __shfl_sync(0xffffffffu, warp_scan(work_of(q, r)), 31);
+    if (lane == 0) wtot[(q0 - q_lo) / kScanThreads * kScanWarps + warp] = tot;
   }
-  need_tables = __syncthreads_or((int)need_tables) != 0;
-  if (HALF && maybe_dup) {  // rare: filter collision or two groups in one bucket -- keep the lowest group only
-    for (int p = 0; p < sB; ++p) {
-      if (p == my_q) continue;
-      const uint2 rp = rng[p];  // non-empty buckets are equal iff their ranges are
-      if (rp.x == my_r.x && rp.y == my_r.y) rng[max(p, my_q)] = make_uint2(0u, 0u);
+  __syncthreads();
+  const u32 flags = s_flags;
+  if (flags & 2u) {  // rare: filter collision or two groups in one bucket -- keep the lowest group only
+    if (maybe_dup) {
+      for (int p = 0; p < sB; ++p) {
+        if (p == my_q) continue;
+        const uint2 rp = rng[p];  // non-empty buckets are equal iff their ranges are
+        if (rp.x == my_r.x && rp.y == my_r.y) rng[max(p, my_q)] = make_uint2(0u, 0u);
+      }
     }
+    __syncthreads();
+    for (int q0 = q_lo; q0 < q_hi; q0 += kScanThreads) {  // the work counts again
+      const int q = q0 + (int)threadIdx.x;
+      const u32 tot = __shfl_sync(0xffffffffu, warp_scan(work_of(q, q < q_hi ? rng[q] : make_uint2(0u, 0u))), 31);
+      if (lane == 0) wtot[(q0 - q_lo) / kScanThreads * kScanWarps + warp] = tot;
+    }
+    __syncthreads();
   }
-  if (need_tables) {
+  if (flags & 1u) {
     const TableOffsets to = table_offsets(g);
     for_each_table_entry(g, lists, to, [&](int t, int, u32 e0, u32 e1) { msk[t] = msk_make<L>(e0 & 0xffu, e1 & 0xffu); });
     if (threadIdx.x == 0) {
@@ -346,56 +380,43 @@ eloc_scan_kernel(const u64 *__restrict__ bra, long long n, GroupView gv, HitRun 
       s_sg[2] = SearchGeom{sB, g.noBB, g.nvBB, to.sb, to.hpb, to.ppb, 0, 0};
     }
   }
-  if (HALF) __syncthreads();  // the duplicate pass may have emptied buckets
-  constexpr int UN = HALF ? kHalfUnroll : kChunkUnroll;
-  if (warp == 0) {  // chunk list of the small alpha-beta groups, in group order; the others go to the long list
-    u32 base = 0, nlong = 0;
-    for (int q0 = g_begin; q0 < ab_end; q0 += 32) {
-      const int q = q0 + lane;
-      u32 nc = 0;
-      bool is_long = false;
-      uint4 ent = make_uint4(0u, 0u, (u32)q, 0u);
-      if (q < ab_end) {
-        const uint2 r = rng[q];
-        ent.x = r.x;
-        ent.y = r.y;
+  // every thread places the work of its groups: chunk list in group order, then the long list
+  {
+    u32 before = 0;  // work of all the (round, warp) pairs before mine
+    int slot = 0;
+    for (int q0 = q_lo; q0 < q_hi; q0 += kScanThreads) {
+      for (int w = 0; w < warp; ++w) before += wtot[slot + w];
+      const int q = q0 + (int)threadIdx.x;
+      const uint2 r = q < q_hi ? rng[q] : make_uint2(0u, 0u);
+      const u32 mine = work_of(q, r);
+      const u32 at = before + warp_scan(mine) - mine;
+      if (mine >> 16) {
+        lgrp[at >> 16] = (unsigned short)q;
+      } else if (mine) {
+        uint4 ent = make_uint4(r.x, r.y, (u32)q, 0u);
         if (L == 1) {
           ent.z = (u32)ypat[q];
           ent.w = (u32)(ypat[q] >> 32);
         }
-        nc = (r.y - r.x + 31u) >> 5;
-        is_long = nc > (u32)kListChunks;
-        if (is_long) nc = 0;
+        for (u32 j = 0; j < mine; ++j) {
+          if (HALF) clist2[(at & 0xffffu) + j] = make_uint2(ent.x, ent.y);
+          else clist4[(at & 0xffffu) + j] = ent;
+          ent.x += 32u;
+        }
       }
-      u32 incl = nc;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const u32 up = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += up;
-      }
-      const u32 at = base + incl - nc;
-      for (u32 j = 0; j < nc; ++j) {
-        if (HALF) clist2[at + j] = make_uint2(ent.x, ent.y);
-        else clist4[at + j] = ent;
-        ent.x += 32u;
-      }
-      base += __shfl_sync(0xffffffffu, incl, 31);
-      const u32 lm = __ballot_sync(0xffffffffu, is_long);
-      if (is_long) lgrp[nlong + (u32)__popc(lm & ((1u << lane) - 1u))] = (unsigned short)q;
-      nlong += (u32)__popc(lm);
+      for (int w = warp; w < kScanWarps; ++w) before += wtot[slot + w];
+      slot += kScanWarps;
     }
-    // the own groups of this slice are walked by one warp each, too
-    if (lane == 0) {
-      for (int q = max(g_begin, sB); q < g_end; ++q) lgrp[nlong++] = (unsigned short)q;
-      s_nlong = (int)nlong;
+    // `before` now is the total: pad the chunk list to a whole number of unrolled iterations with empty chunks
+    const u32 nch = before & 0xffffu, padded = (nch + (u32)UN - 1u) / (u32)UN * (u32)UN;
+    if (threadIdx.x < padded - nch) {
+      if (HALF) clist2[nch + threadIdx.x] = make_uint2(0u, 0u);
+      else clist4[nch + threadIdx.x] = make_uint4(0u, 0u, (u32)g_begin, 0u);
     }
-    // pad to a whole number of unrolled iterations with empty chunks (first == end)
-    const u32 padded = (base + (u32)UN - 1u) / (u32)UN * (u32)UN;
-    if ((u32)lane < padded - base) {
-      if (HALF) clist2[base + lane] = make_uint2(0u, 0u);
-      else clist4[base + lane] = make_uint4(0u, 0u, (u32)g_begin, 0u);
+    if (threadIdx.x == 0) {
+      s_nchunks = (int)padded;
+      s_nlong = (int)(before >> 16);
     }
-    if (lane == 0) s_nchunks = (int)padded;
   }
   __syncthreads();
 
@@ -535,10 +556,31 @@ eloc_eval_kernel(const u64 *__restrict__ bra, long long n, const double *__restr
     const u32 sp = self_pos[s];
     if (sp != kNoSelf) p0 = load_psi<CPLX>(psi, (long long)__ldg(gv.rows[0] + sp));
     if (lane == 0) accumulate<CPLX>(acc, p0, p0, hii[s]);  // row 0: (psi0/psi0) * H_xx
-    for (int w = 0; w < nruns; ++w) {
-      const HitRun run = my_runs[w];
-      for (u32 e = lane; e < run.cnt; e += 32) {
-        const u32 h = hits[run.off + e];
+    // the sample's runs back to back: lane r holds run r and an inclusive prefix of the counts, so the
+    // whole list is walked 32 hits at a time whatever the runs' lengths (32 runs per round)
+    for (int r0 = 0; r0 < nruns; r0 += 32) {
+      HitRun mine = {0u, 0u};
+      if (r0 + lane < nruns) mine = my_runs[r0 + lane];
+      u32 incl = mine.cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const u32 up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += up;
+      }
+      const u32 total = __shfl_sync(0xffffffffu, incl, 31);
+      for (u32 e0 = 0; e0 < total; e0 += 32) {
+        const u32 e = e0 + (u32)lane;
+        int r = 0;  // the run that holds hit e: the first one whose inclusive prefix exceeds e
+#pragma unroll
+        for (int step = 16; step > 0; step >>= 1) {
+          const u32 v = __shfl_sync(0xffffffffu, incl, r + step - 1);
+          if (v <= e) r += step;
+        }
+        r = min(r, 31);
+        const u32 r_incl = __shfl_sync(0xffffffffu, incl, r), r_cnt = __shfl_sync(0xffffffffu, mine.cnt, r);
+        const u32 r_off = __shfl_sync(0xffffffffu, mine.off, r);
+        if (e >= total) continue;
+        const u32 h = hits[r_off + (e - (r_incl - r_cnt))];
         const bool grouping = (h & kHitA) != 0u;
         const u32 pos = HALF ? (h & kHitPos) : (h & ~kHitA);
         const Onv<L> y = load_onv<L>((grouping ? gv.keys[1] : gv.keys[0]) + (size_t)pos * L);
@@ -625,7 +667,8 @@ static int launch_eloc_LC(const u64 *bra, long long n, const double *h1e, const 
   HitRun *runs = reinterpret_cast<HitRun *>(scratch + lay.runs);
   u32 *cursor = reinterpret_cast<u32 *>(scratch + lay.cursor);
   u32 *hits = reinterpret_cast<u32 *>(scratch + lay.hits);
-  const size_t smem = scan_smem(g).total;
+  const ScanSmem sm = scan_smem(g);
+  const size_t smem = sm.total;
   if (smem > 48 * 1024 &&
       cudaFuncSetAttribute(eloc_scan_kernel<L, HALF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return check_launch("eloc_scan_kernel smem opt-in");
@@ -636,7 +679,7 @@ static int launch_eloc_LC(const u64 *bra, long long n, const double *h1e, const 
     if (cudaMemsetAsync(cursor, 0, 4, st) != cudaSuccess) return check_launch("eloc cursor memset");
     if (cudaMemsetAsync(self_pos, 0xff, 4 * (size_t)nb, st) != cudaSuccess) return check_launch("eloc self memset");
     eloc_scan_kernel<L, HALF><<<(unsigned)(nb * splits), kScanThreads, smem, st>>>(bra + b0 * L, nb, gv, runs, hits, self_pos, cursor,
-                                                                              (u32)lay.hit_cap, splits, g);
+                                                                              (u32)lay.hit_cap, splits, g, sm);
     count_launch();
     if (int rc = check_launch("eloc_scan_kernel")) return rc;
     const unsigned eb = (unsigned)((nb + kEvalThreads / 32 - 1) / (kEvalThreads / 32));
