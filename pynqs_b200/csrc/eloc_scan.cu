@@ -35,8 +35,7 @@
 
 namespace pynqs {
 
-constexpr int kScanThreads = 256;  // scan kernel: 8 warps per CTA
-constexpr int kScanWarps = kScanThreads / 32;
+constexpr int kMaxScanWarps = 8;   // scan kernel: 2, 4 or 8 warps per CTA, by the number of groups of a sample
 constexpr int kQueue = 512;        // hits per warp before the sample falls back to the full route
 constexpr int kEvalThreads = 128;  // eval kernel: 4 samples per CTA
 constexpr u32 kOverflow = 0x80000000u;
@@ -222,12 +221,13 @@ __device__ __noinline__ u32 search_bucket(const u64 *__restrict__ keys, u32 s, u
 constexpr int kListChunks = 4;     // groups of up to kListChunks * 32 keys go to the flat chunk list
 constexpr int kChunkUnroll = 4;    // independent key loads in flight per lane (full keys)
 constexpr int kHalfUnroll = 8;     // ... (folded 32-bit strings)
+constexpr int kDupList = 32;       // suspects checked exactly (more: every group is checked)
 constexpr int kDupWords = 512;     // 16384-bit filter for "two of my groups share a bucket"
 
 struct ScanSmem {
   u32 ypat, msk, rng, dup, lgrp, clist, queues, total;
 };
-__host__ __device__ inline ScanSmem scan_smem(const ExcGeom &g) {
+__host__ __device__ inline ScanSmem scan_smem(const ExcGeom &g, int warps) {
   const size_t sB = (size_t)g.noB * g.nvB, nG = sB + 2;
   ScanSmem m;
   size_t o = (sizeof(OrbLists) + 15) & ~(size_t)15;
@@ -244,7 +244,7 @@ __host__ __device__ inline ScanSmem scan_smem(const ExcGeom &g) {
   m.clist = (u32)o;
   o += 16 * (sB * kListChunks + 8);
   m.queues = (u32)o;
-  m.total = (u32)(o + sizeof(u32) * kQueue * kScanWarps);
+  m.total = (u32)(o + sizeof(u32) * kQueue * warps);
   return m;
 }
 
@@ -257,8 +257,8 @@ constexpr u32 kHitA = 0x80000000u, kHitOwn = 0x40000000u, kHitPos = 0x3fffffffu;
 // larger groups are walked (or searched) by one warp each.
 // HALF (L = 1, N < 2^30): the test reads the folded 32-bit strings; a key that passes may sit in the bucket
 // by hash collision, which the eval kernel detects on the full key.
-template <int L, bool HALF>
-__global__ void __launch_bounds__(kScanThreads)
+template <int L, bool HALF, int THREADS>
+__global__ void __launch_bounds__(THREADS)
 eloc_scan_kernel(const u64 *__restrict__ bra, long long n, GroupView gv, HitRun *__restrict__ runs, u32 *__restrict__ hits,
                  u32 *__restrict__ self_pos, u32 *cursor, u32 hit_cap, int splits, ExcGeom g, ScanSmem sm) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -273,8 +273,10 @@ eloc_scan_kernel(const u64 *__restrict__ bra, long long n, GroupView gv, HitRun 
   uint2 *clist2 = reinterpret_cast<uint2 *>(smem_raw + sm.clist);  // HALF: {first key, bucket end}
   u32 *queues = reinterpret_cast<u32 *>(smem_raw + sm.queues);
   __shared__ int s_nchunks, s_nlong;
-  __shared__ u32 s_flags;
-  __shared__ u32 wtot[kScanWarps * 10];  // work per (round of 256 groups, warp); nG <= 2306 -> 10 rounds
+  __shared__ u32 s_flags, s_ndup;
+  __shared__ unsigned short s_dupq[kDupList];
+  constexpr int kScanThreads = THREADS, kScanWarps = THREADS / 32;
+  __shared__ u32 wtot[80];  // work per (round of THREADS groups, warp); nG <= 2306 -> at most 37 x 2 entries
   __shared__ SearchGeom s_sg[3];
 
   const long long s = splits == 1 ? (long long)blockIdx.x : (long long)(blockIdx.x / (unsigned)splits);
@@ -294,7 +296,7 @@ eloc_scan_kernel(const u64 *__restrict__ bra, long long n, GroupView gv, HitRun 
   if (HALF) {
     for (int t = threadIdx.x; t < kDupWords; t += kScanThreads) dupf[t] = 0u;
   }
-  if (threadIdx.x == 0) s_flags = 0u;
+  if (threadIdx.x == 0) s_flags = s_ndup = 0u;
   __syncthreads();
 
   // ---- the groups of this slice: pattern and bucket of each ---------------------------------------------------
@@ -320,9 +322,6 @@ eloc_scan_kernel(const u64 *__restrict__ bra, long long n, GroupView gv, HitRun 
     }
     return v;
   };
-  bool maybe_dup = false;
-  uint2 my_r = make_uint2(0u, 0u);
-  int my_q = -1;
   for (int q0 = q_lo; q0 < q_hi; q0 += kScanThreads) {
     const int q = q0 + (int)threadIdx.x;
     uint2 r = make_uint2(0u, 0u);
@@ -342,12 +341,16 @@ eloc_scan_kernel(const u64 *__restrict__ bra, long long n, GroupView gv, HitRun 
       for (int w = 0; w < L; ++w) ypat[q * L + w] = y.w[w];
       const u32 size = r.y - r.x;
       if (size > (q < sB ? big_ab : (q == sB ? big_own_b : big_own_a))) atomicOr(&s_flags, 1u);  // searched: needs the tables
-      if (HALF && q < sB && size && size <= big_ab) {  // the folded test cannot tell two beta strings in one bucket
-        my_r = r;  // apart: a bucket must be WALKED for only one of the groups that map to it (searches are exact
-        my_q = q;  // per group and stay).  L = 1: at most 256 alpha-beta groups, one per thread.
+      if (HALF && q < sB && size && size <= big_ab) {
+        // the folded test cannot tell two beta strings in one bucket apart: a bucket must be WALKED for only one
+        // of the groups that map to it (searches are exact per group and stay).  Suspects (second arrival at a
+        // bit of the filter) are listed and checked exactly below.
         const u32 bit = 1u << (bkt & 31u);
-        maybe_dup = (atomicOr(&dupf[(bkt >> 5) & (kDupWords - 1)], bit) & bit) != 0u;
-        if (maybe_dup) atomicOr(&s_flags, 2u);
+        if (atomicOr(&dupf[(bkt >> 5) & (kDupWords - 1)], bit) & bit) {
+          const u32 at = atomicAdd(&s_ndup, 1u);
+          if (at < (u32)kDupList) s_dupq[at] = (unsigned short)q;
+          atomicOr(&s_flags, 2u);
+        }
       }
     }
     const u32 tot = __shfl_sync(0xffffffffu, warp_scan(work_of(q, r)), 31);
@@ -356,11 +359,30 @@ eloc_scan_kernel(const u64 *__restrict__ bra, long long n, GroupView gv, HitRun 
   __syncthreads();
   const u32 flags = s_flags;
   if (flags & 2u) {  // rare: filter collision or two groups in one bucket -- keep the lowest group only
-    if (maybe_dup) {
-      for (int p = 0; p < sB; ++p) {
-        if (p == my_q) continue;
-        const uint2 rp = rng[p];  // non-empty buckets are equal iff their ranges are
-        if (rp.x == my_r.x && rp.y == my_r.y) rng[max(p, my_q)] = make_uint2(0u, 0u);
+    const u32 nd = s_ndup;
+    if (nd <= (u32)kDupList) {
+      // one of the groups of a shared bucket arrived first and is not listed, so a suspect clears the HIGHER of
+      // every equal pair it finds; the lowest group of a bucket is never cleared and everyone else matches it
+      for (u32 i = threadIdx.x; i < nd; i += kScanThreads) {
+        const int q = s_dupq[i];
+        const uint2 rq = rng[q];
+        if (rq.x == rq.y) continue;  // already cleared by another suspect
+        for (int p = 0; p < sB; ++p) {
+          const uint2 rp = rng[p];  // non-empty buckets are equal iff their ranges are
+          if (p != q && rp.x == rq.x && rp.y == rq.y) rng[max(p, q)] = make_uint2(0u, 0u);
+        }
+      }
+    } else {  // list overflow: every group looks for a lower group with the same bucket
+      for (int q = threadIdx.x; q < sB; q += kScanThreads) {
+        const uint2 rq = rng[q];
+        if (rq.x == rq.y || rq.y - rq.x > big_ab) continue;
+        for (int p = 0; p < q; ++p) {
+          const uint2 rp = rng[p];
+          if (rp.x == rq.x && rp.y == rq.y) {
+            rng[q] = make_uint2(0u, 0u);
+            break;
+          }
+        }
       }
     }
     __syncthreads();
@@ -526,13 +548,14 @@ __global__ void __launch_bounds__(kEvalThreads)
 eloc_eval_kernel(const u64 *__restrict__ bra, long long n, const double *__restrict__ h1e, const double *__restrict__ h2e,
                  const u64 *__restrict__ key, const double *__restrict__ psi, long long N, GroupView gv,
                  const HitRun *__restrict__ runs, const u32 *__restrict__ hits, const u32 *__restrict__ self_pos,
-                 const double *__restrict__ hii, double *__restrict__ eloc, double *__restrict__ psi0_out, int splits, ExcGeom g) {
+                 const double *__restrict__ hii, double *__restrict__ eloc, double *__restrict__ psi0_out, int splits, int scan_warps,
+                 ExcGeom g) {
   __shared__ OrbLists s_lists[kEvalThreads / 32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long s = (long long)blockIdx.x * (kEvalThreads / 32) + warp;
   if (s >= n) return;
   const Onv<L> x = load_onv<L>(bra + s * L);
-  const int nruns = splits * kScanWarps;
+  const int nruns = splits * scan_warps;
   const HitRun *my_runs = runs + s * nruns;
   bool redo = false;
   for (int w = lane; w < nruns; w += 32) redo |= (my_runs[w].cnt & kOverflow) != 0;
@@ -618,10 +641,18 @@ eloc_eval_kernel(const u64 *__restrict__ bra, long long n, const double *__restr
 
 // ---- host side --------------------------------------------------------------------------------------------
 // splits: CTAs per sample -- more than one only when there are too few samples to fill the GPU
-static int scan_splits(long long n, int n_groups) {
+static int scan_threads(int n_groups) {
+  if (const char *e = getenv("PYNQS_SCAN_THREADS")) {  // experiments only
+    const int t = atoi(e);
+    if (t == 64 || t == 128 || t == 256) return t;
+  }
+  return n_groups <= 192 ? 128 : 256;
+}
+
+static int scan_splits(long long n, int n_groups, int warps) {
   if (n <= 0) return 1;
   long long want = (148LL * 8 + n - 1) / n;
-  const long long cap = n_groups / kScanWarps > 1 ? n_groups / kScanWarps : 1;
+  const long long cap = n_groups / warps > 1 ? n_groups / warps : 1;
   if (want > cap) want = cap;
   return (int)(want < 1 ? 1 : want);
 }
@@ -630,6 +661,7 @@ struct ElocScratch {
   long long hii, self_pos, runs, cursor, hits, total;
   long long hit_cap, batch;
   int splits;  // same for every batch of the call (sized for the first, largest one)
+  int warps;   // warps per scan CTA
 };
 
 static ElocScratch eloc_scratch_layout(long long n, const ExcGeom &g) {
@@ -641,11 +673,12 @@ static ElocScratch eloc_scratch_layout(long long n, const ExcGeom &g) {
   l.batch = (1LL << 28) / per_sample;
   l.batch = l.batch < 1024 ? 1024 : (l.batch > (1LL << 18) ? (1LL << 18) : l.batch);
   const long long nb = n < l.batch ? n : l.batch;
-  l.splits = scan_splits(nb, g.noB * g.nvB + 2);
+  l.warps = scan_threads(g.noB * g.nvB + 2) / 32;
+  l.splits = scan_splits(nb, g.noB * g.nvB + 2, l.warps);
   l.hii = 0;
   l.self_pos = (l.hii + 8 * n + 15) / 16 * 16;
   l.runs = (l.self_pos + 4 * nb + 15) / 16 * 16;
-  l.cursor = l.runs + (long long)sizeof(HitRun) * nb * l.splits * kScanWarps;
+  l.cursor = l.runs + (long long)sizeof(HitRun) * nb * l.splits * kMaxScanWarps;
   l.hits = l.cursor + 256;
   l.hit_cap = nb * per_sample + 65536;
   if (l.hit_cap > 0x7fffffffLL) l.hit_cap = 0x7fffffffLL;
@@ -667,10 +700,10 @@ static int launch_eloc_LC(const u64 *bra, long long n, const double *h1e, const 
   HitRun *runs = reinterpret_cast<HitRun *>(scratch + lay.runs);
   u32 *cursor = reinterpret_cast<u32 *>(scratch + lay.cursor);
   u32 *hits = reinterpret_cast<u32 *>(scratch + lay.hits);
-  const ScanSmem sm = scan_smem(g);
+  const ScanSmem sm = scan_smem(g, lay.warps);
   const size_t smem = sm.total;
-  if (smem > 48 * 1024 &&
-      cudaFuncSetAttribute(eloc_scan_kernel<L, HALF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+  auto scan = lay.warps == 2 ? eloc_scan_kernel<L, HALF, 64> : (lay.warps == 4 ? eloc_scan_kernel<L, HALF, 128> : eloc_scan_kernel<L, HALF, 256>);
+  if (smem > 48 * 1024 && cudaFuncSetAttribute(scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return check_launch("eloc_scan_kernel smem opt-in");
   const int w = CPLX ? 2 : 1;
   for (long long b0 = 0; b0 < n; b0 += lay.batch) {
@@ -678,13 +711,13 @@ static int launch_eloc_LC(const u64 *bra, long long n, const double *h1e, const 
     const int splits = lay.splits;
     if (cudaMemsetAsync(cursor, 0, 4, st) != cudaSuccess) return check_launch("eloc cursor memset");
     if (cudaMemsetAsync(self_pos, 0xff, 4 * (size_t)nb, st) != cudaSuccess) return check_launch("eloc self memset");
-    eloc_scan_kernel<L, HALF><<<(unsigned)(nb * splits), kScanThreads, smem, st>>>(bra + b0 * L, nb, gv, runs, hits, self_pos, cursor,
+    scan<<<(unsigned)(nb * splits), lay.warps * 32, smem, st>>>(bra + b0 * L, nb, gv, runs, hits, self_pos, cursor,
                                                                               (u32)lay.hit_cap, splits, g, sm);
     count_launch();
     if (int rc = check_launch("eloc_scan_kernel")) return rc;
     const unsigned eb = (unsigned)((nb + kEvalThreads / 32 - 1) / (kEvalThreads / 32));
     eloc_eval_kernel<L, CPLX, HALF><<<eb, kEvalThreads, 0, st>>>(bra + b0 * L, nb, h1e, h2e, key, psi, N, gv, runs, hits, self_pos,
-                                                            hii + b0, eloc + b0 * w, psi0 + b0 * w, splits, g);
+                                                            hii + b0, eloc + b0 * w, psi0 + b0 * w, splits, lay.warps, g);
     count_launch();
     if (int rc = check_launch("eloc_eval_kernel")) return rc;
   }
