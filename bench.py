@@ -260,7 +260,7 @@ def run_ours(args):
             k, p = d_keys, d_psi
         uniq, wf, cnt = exchange_unique_samples(k, p, None, disjoint=True, equal_sizes=equal_sizes)
         ev[1].record()
-        lut = WavefunctionLUT(uniq, wf, SORB, dev, sort=not args.unsorted_table, rank=rank, world_size=world)
+        lut = WavefunctionLUT(uniq, wf, SORB, dev, rank=rank, world_size=world)
         gidx = lut.group_index  # built here, inside the table phase
         b, e = rank_slice(uniq.size(0), rank, world)
         x = uniq[b:e]
@@ -324,14 +324,14 @@ def run_ours(args):
     peak, peak_src = hbm_peak_gbs()
     achieved = B * k_n / (k_ms * 1e-3) / 1e9
     prof = load_profile_numbers()
-    roof = {"bound": "hbm", "kernel": "eloc_filter_kernel<1> (+ eloc_eval_kernel, diag_kernel): one-pass sample-space E_loc",
+    roof = {"bound": "hbm", "kernel": "eloc_scan_kernel<1> (+ eloc_eval_kernel, diag_kernel): one-pass sample-space E_loc",
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "traffic": prof.get("eloc_dram_bytes_per_sample"), "traffic_unit": "DRAM bytes per sample (ncu, profiles/)",
             "peak_source": peak_src, "algorithmic_bytes_per_sample": B, "samples_per_launch": k_n, "kernel_ms": k_ms,
             "note": "equivalent-bytes roofline per SURVEY.md 8(d): the one-pass kernels never write comb/Hmat/idx, so "
-                    "'achieved' = API-path bytes (fused + lut, 259.9 KB/sample) / time and may exceed the HBM peak; their real "
-                    "bound is L1/LSU wavefronts + issue slots (profiles/). The kernels that really move those bytes are in "
-                    "'roofline_hbm_kernels'."}
+                    "'achieved' = API-path bytes (fused + lut, 259.9 KB/sample) / time and exceeds the HBM peak; they scan the "
+                    "string-grouped table copies out of L2 and their real bound is the issue slots (profiles/). The kernels "
+                    "that really move the API-path bytes are in 'roofline_hbm_kernels'."}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -341,10 +341,9 @@ def run_ours(args):
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": {"workload": "fe2s2_cas30e20o_40sorb_15a15b", "sorb": SORB, "noA": NOA, "noB": NOB, "M": M, "n_samples": n_total,
-                   "lut_keys": n_total, "integrals": "random 8-fold symmetric, seed 7", "method": "sample-space, one-pass kernel",
+                   "lut_keys": n_total, "integrals": "random 8-fold symmetric, seed 7", "method": "sample-space, one-pass kernels (group scan)",
                    "l2": "flushed between timed steps (512 MiB write)", "parallelism": f"samples sharded over {world} rank(s)",
-                   "step": ("exchange + lookup index + E_loc + statistics" if args.unsorted_table
-                            else "exchange + table sort + lookup index + E_loc + statistics")},
+                   "step": "exchange + table sort + grouped table + E_loc + statistics"},
         "roofline": roof,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n_total * 16), "d2h_bytes_per_step": int(n_total * 8 + 40 * world),
                 "ms_per_step": e2e_ms / args.steps},
@@ -420,8 +419,6 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--samples", type=int, default=1_000_000)
     ap.add_argument("--ref-samples", type=int, default=4096, help="samples per step of the reference CPU arm")
-    ap.add_argument("--unsorted-table", action="store_true",
-                    help="skip the key sort: the one-pass op only needs the index, not the reference's sorted order")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-api-path", action="store_true")
     args = ap.parse_args()

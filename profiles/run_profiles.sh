@@ -6,7 +6,7 @@ TAG=${1:-r01}
 mkdir -p gpurun_out
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${TAG}_launches.csv \
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/${TAG}_launches_bench.log 2>&1
-ncu --set full --clock-control none --import-source on -k 'regex:eloc_filter_kernel|eloc_eval_kernel' -s 2 -c 2 -f -o gpurun_out/${TAG}_eloc \
+ncu --set full --clock-control none --import-source on -k 'regex:eloc_scan_kernel|eloc_eval_kernel' -s 2 -c 2 -f -o gpurun_out/${TAG}_eloc \
     python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-api-path > gpurun_out/${TAG}_eloc.log 2>&1
 ncu --set full --clock-control none --import-source on -k 'regex:enumerate_kernel|lut_indexed_kernel' -s 4 -c 2 -f -o gpurun_out/${TAG}_api \
     python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/${TAG}_api.log 2>&1
