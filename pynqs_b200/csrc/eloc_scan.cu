@@ -576,6 +576,7 @@ eloc_eval_kernel(const u64 *__restrict__ bra, long long n, const double *__restr
       if (id >= 0) accumulate<CPLX>(acc, load_psi<CPLX>(psi, id), p0, exc_element<L, double>(x, e, h1e, h2e, g.sorb));
     }
   } else {
+    bool have_lists = false;
     const u32 sp = self_pos[s];
     if (sp != kNoSelf) p0 = load_psi<CPLX>(psi, (long long)__ldg(gv.rows[0] + sp));
     if (lane == 0) accumulate<CPLX>(acc, p0, p0, hii[s]);  // row 0: (psi0/psi0) * H_xx
@@ -602,22 +603,45 @@ eloc_eval_kernel(const u64 *__restrict__ bra, long long n, const double *__restr
         r = min(r, 31);
         const u32 r_incl = __shfl_sync(0xffffffffu, incl, r), r_cnt = __shfl_sync(0xffffffffu, mine.cnt, r);
         const u32 r_off = __shfl_sync(0xffffffffu, mine.off, r);
-        if (e >= total) continue;
-        const u32 h = hits[r_off + (e - (r_incl - r_cnt))];
-        const bool grouping = (h & kHitA) != 0u;
-        const u32 pos = HALF ? (h & kHitPos) : (h & ~kHitA);
-        const Onv<L> y = load_onv<L>((grouping ? gv.keys[1] : gv.keys[0]) + (size_t)pos * L);
-        if (HALF) {  // the scan tested one folded string only: class of the full key vs the scan it came from
-          const u64 d = y.w[0] ^ x.w[0];
-          const int na = __popcll(d & kEven), nb = __popcll(d & kOdd);
-          bool ok;
-          if (!(h & kHitOwn)) ok = na == 2 && nb == 2;               // alpha-beta double (bucket of a beta single)
-          else if (!grouping) ok = nb == 0 && (na == 2 || na == 4);  // own beta string
-          else ok = na == 0 && (nb == 2 || nb == 4);                 // own alpha string
-          if (!ok) continue;
+        // (no early exits: the ballot below needs every lane)
+        Onv<L> y = x;
+        long long id = 0;
+        int kind = 0;  // 1 single, 2 double, 0 nothing to add
+        if (e < total) {
+          const u32 h = hits[r_off + (e - (r_incl - r_cnt))];
+          const bool grouping = (h & kHitA) != 0u;
+          const u32 pos = HALF ? (h & kHitPos) : (h & ~kHitA);
+          y = load_onv<L>((grouping ? gv.keys[1] : gv.keys[0]) + (size_t)pos * L);
+          bool ok = true;
+          if (HALF) {  // the scan tested one folded string only: class of the full key vs the scan it came from
+            const u64 d = y.w[0] ^ x.w[0];
+            const int na = __popcll(d & kEven), nb = __popcll(d & kOdd);
+            if (!(h & kHitOwn)) ok = na == 2 && nb == 2;               // alpha-beta double (bucket of a beta single)
+            else if (!grouping) ok = nb == 0 && (na == 2 || na == 4);  // own beta string
+            else ok = na == 0 && (nb == 2 || nb == 4);                 // own alpha string
+          }
+          if (ok) {
+            kind = excitation_class<L>(x, y);
+            id = (long long)__ldg((grouping ? gv.rows[1] : gv.rows[0]) + pos);
+          }
         }
-        const long long id = (long long)__ldg((grouping ? gv.rows[1] : gv.rows[0]) + pos);
-        accumulate<CPLX>(acc, load_psi<CPLX>(psi, id), p0, rederived_element<L, double>(x, y, h1e, h2e, g.sorb, g.nele));
+        if (kind == 2) accumulate<CPLX>(acc, load_psi<CPLX>(psi, id), p0, rederived_element<L, double>(x, y, h1e, h2e, g.sorb, g.nele));
+        // single excitations (rare): one at a time by the whole warp, terms gathered in parallel
+        u32 pend = __ballot_sync(0xffffffffu, kind == 1);
+        while (pend) {
+          const int src = __ffs(pend) - 1;
+          pend &= pend - 1u;
+          if (!have_lists) {
+            build_lists<L>(x, g.sorb, g.noA, g.noB, s_lists[warp], lane);
+            __syncwarp();
+            have_lists = true;
+          }
+          Onv<L> ys;
+#pragma unroll
+          for (int w = 0; w < L; ++w) ys.w[w] = __shfl_sync(0xffffffffu, y.w[w], src);
+          const double v = single_element_warp<L, double>(x, ys, h1e, h2e, g.sorb, s_lists[warp].occ_order, s_lists[warp].n_occ);
+          if (lane == src) accumulate<CPLX>(acc, load_psi<CPLX>(psi, id), p0, v);
+        }
       }
     }
   }

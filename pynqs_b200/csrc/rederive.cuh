@@ -57,4 +57,51 @@ __device__ __forceinline__ T rederived_element(const Onv<L> &x, const Onv<L> &y,
   return (T)0.0;
 }
 
+// class of the pair from the popcounts of bra-only / ket-only orbitals: 1 single, 2 double, 0 anything else
+// (the diagonal included -- callers treat x == y themselves)
+template <int L>
+__device__ __forceinline__ int excitation_class(const Onv<L> &x, const Onv<L> &y) {
+  int nc = 0, na = 0;
+#pragma unroll
+  for (int i = 0; i < L; ++i) {
+    const u64 d = x.w[i] ^ y.w[i];
+    nc += __popcll(d & x.w[i]);
+    na += __popcll(d & y.w[i]);
+  }
+  return (nc == 1 && na == 1) ? 1 : ((nc == 2 && na == 2) ? 2 : 0);
+}
+
+// Single excitation x -> y evaluated by a whole warp (all lanes pass the same x, y): the two-electron terms
+// of cpp_src/cpu/hamiltonian.cpp:52-72 are gathered one per lane and then added in the reference's order
+// (occ_order: words ascending, bits descending) through shuffles -- the same additions in the same order as
+// exc_element, without its chain of dependent loads.  Every lane returns the element.
+template <int L, typename T>
+__device__ __forceinline__ T single_element_warp(const Onv<L> &x, const Onv<L> &y, const T *__restrict__ h1e,
+                                                 const T *__restrict__ h2e, int sorb, const unsigned char *occ_order, int n_occ) {
+  const int lane = threadIdx.x & 31;
+  Onv<L> cre, ann;
+#pragma unroll
+  for (int i = 0; i < L; ++i) {
+    const u64 d = x.w[i] ^ y.w[i];
+    cre.w[i] = d & x.w[i];
+    ann.w[i] = d & y.w[i];
+  }
+  const u32 h = (u32)pop_highest<L>(cre), p = (u32)pop_highest<L>(ann);
+  T v = (T)0.0;
+  v += __ldg(h1e + (size_t)p * sorb + h);
+  for (int j0 = 0; j0 < n_occ; j0 += 32) {
+    const int j = j0 + lane;
+    T t = (T)0.0;
+    if (j < n_occ) {
+      const u32 k = occ_order[j];
+      t = two_body<T>(h2e, h, k, p, k);
+    }
+    const int cnt = min(32, n_occ - j0);
+    for (int l = 0; l < cnt; ++l) v += __shfl_sync(0xffffffffu, t, l);
+  }
+  const int sg = (count_below<L>(x, (int)h) ^ count_below<L>(x, (int)p) ^ (int)(h < p)) & 1;
+  v *= sg ? (T)-1.0 : (T)1.0;
+  return v;
+}
+
 }  // namespace pynqs
