@@ -13,7 +13,11 @@ def main(path, per=1, lo=None, hi=None):
     hdr = next(r for r in rows if "Instructions Executed" in r)
     hi_ = rows.index(hdr)
     ie, src, smp = hdr.index("Instructions Executed"), hdr.index("Source"), hdr.index("# Samples")
-    body = [r for r in rows[hi_ + 1:] if len(r) == len(hdr)]
+    body = []
+    for r in rows[hi_ + 1:]:  # first kernel of the report only
+        if len(r) != len(hdr) or r == hdr:
+            break
+        body.append(r)
     T = sum(int(r[ie]) for r in body)
     S = sum(int(r[smp]) for r in body)
     print(f"total warp-instructions {T} ({T / per:.0f} per unit), stall samples {S}, SASS lines {len(body)}")
