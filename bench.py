@@ -324,10 +324,14 @@ def run_ours(args):
     peak, peak_src = hbm_peak_gbs()
     achieved = B * k_n / (k_ms * 1e-3) / 1e9
     prof = load_profile_numbers()
-    roof = {"bound": "hbm", "kernel": "eloc_scan_kernel<1> (+ eloc_eval_kernel, diag_kernel): one-pass sample-space E_loc",
+    per_sample_dram = prof.get("eloc_dram_bytes_per_sample")
+    roof = {"bound": "hbm", "kernel": "eloc_scan_kernel<1,folded,128> (+ eloc_eval_kernel, diag_kernel): one-pass sample-space E_loc",
+            "launch": "one pynqs_eloc_sample_space call on this rank's samples = 1 diag kernel + one scan and one eval kernel per batch of <= 136 400 samples",
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": prof.get("eloc_dram_bytes_per_sample"), "traffic_unit": "DRAM bytes per sample (ncu, profiles/)",
-            "peak_source": peak_src, "algorithmic_bytes_per_sample": B, "samples_per_launch": k_n, "kernel_ms": k_ms,
+            "traffic": per_sample_dram * k_n if per_sample_dram else None,
+            "traffic_note": "DRAM bytes per call from ncu (profiles/r01/traffic.json: %s B/sample): the table copies stay in L2" % per_sample_dram,
+            "peak_source": peak_src, "algorithmic_bytes_per_sample": B, "algorithmic_bytes_per_launch": B * k_n,
+            "samples_per_launch": k_n, "kernel_ms": k_ms,
             "note": "equivalent-bytes roofline per SURVEY.md 8(d): the one-pass kernels never write comb/Hmat/idx, so "
                     "'achieved' = API-path bytes (fused + lut, 259.9 KB/sample) / time and exceeds the HBM peak; they scan the "
                     "string-grouped table copies out of L2 and their real bound is the issue slots (profiles/). The kernels "
