@@ -309,6 +309,115 @@ diag_kernel(const u64 *__restrict__ bra, const T *__restrict__ h1e, const T *__r
   out[s * stride] = diag_element<L, T>(x, h1e, h2e, sorb, nele);
 }
 
+// Same sum from a per-CTA table in shared memory: D2[p][q] = <pq||pq> and D1[p] = h1e[p,p] are gathered ONCE per
+// CTA (sorb^2 entries) instead of once per sample and term, so a term is a shared-memory load and an add --
+// the same values added in the same order as diag_element (cpp_src/cpu/hamiltonian.cpp:33-50).  Each thread
+// takes kDiagPerThread samples.  Used when the table fits in shared memory (sorb <= ~160 for float64).
+constexpr int kDiagThreads = 128;
+
+template <int L, typename T>
+__global__ void __launch_bounds__(kDiagThreads)
+diag_table_kernel(const u64 *__restrict__ bra, const T *__restrict__ h1e, const T *__restrict__ h2e, T *__restrict__ out,
+                  long long n, long long stride, int sorb, int nele, int per_thread) {
+  extern __shared__ __align__(16) unsigned char diag_smem[];
+  T *d2 = reinterpret_cast<T *>(diag_smem);
+  T *d1 = d2 + sorb * sorb;
+  for (int t = threadIdx.x; t < sorb * sorb; t += kDiagThreads) {
+    const u32 p = (u32)t / (u32)sorb, q = (u32)t - p * (u32)sorb;
+    d2[t] = two_body<T>(h2e, p, q, p, q);
+  }
+  for (int p = threadIdx.x; p < sorb; p += kDiagThreads) d1[p] = __ldg(h1e + (size_t)p * sorb + p);
+  __syncthreads();
+  const long long first = (long long)blockIdx.x * (kDiagThreads * per_thread) + threadIdx.x;
+  for (int it = 0; it < per_thread; ++it) {
+    const long long s = first + (long long)it * kDiagThreads;
+    if (s >= n) return;
+    const Onv<L> x = load_onv<L>(bra + s * L);
+    int occ = 0;
+#pragma unroll
+    for (int i = 0; i < L; ++i) occ += __popcll(x.w[i]);
+    T v = (T)0.0;
+    if (occ == nele) {
+      // every occupied orbital p ascending, and for each the occupied q < p ascending: 32-bit words, lowest
+      // set bit first (w & (w - 1) clears it)
+#pragma unroll
+      for (int hp = 0; hp < 2 * L; ++hp) {
+        u32 w = (u32)(x.w[hp >> 1] >> (32 * (hp & 1)));
+        while (w) {
+          const u32 b = (u32)__ffs((int)w) - 1u;
+          w &= w - 1u;
+          const u32 p = 32u * hp + b;
+          v += d1[p];
+          const T *row = d2 + p * (u32)sorb;
+#pragma unroll
+          for (int hq = 0; hq <= hp; ++hq) {
+            u32 u = (u32)(x.w[hq >> 1] >> (32 * (hq & 1)));
+            if (hq == hp) u &= (1u << b) - 1u;
+            const T *rq = row + 32 * hq;
+            while (u) {
+              const u32 q = (u32)__ffs((int)u) - 1u;
+              u &= u - 1u;
+              v += rq[q];
+            }
+          }
+        }
+      }
+    } else {  // electron count differs from nele: the reference's zero-padded list, term by term
+      Onv<L> outer = x;
+      for (int a = 0; a < nele; ++a) {
+        u32 p = 0;
+#pragma unroll
+        for (int i = 0; i < L; ++i) {
+          if (outer.w[i]) {
+            const int b = __ffsll((long long)outer.w[i]) - 1;
+            outer.w[i] ^= 1ull << b;
+            p = (u32)(64 * i + b);
+            break;
+          }
+        }
+        v += d1[p];
+        Onv<L> inner = x;
+        for (int c = 0; c < a; ++c) {
+          u32 q = 0;
+#pragma unroll
+          for (int i = 0; i < L; ++i) {
+            if (inner.w[i]) {
+              const int b = __ffsll((long long)inner.w[i]) - 1;
+              inner.w[i] ^= 1ull << b;
+              q = (u32)(64 * i + b);
+              break;
+            }
+          }
+          v += d2[p * (u32)sorb + q];
+        }
+      }
+    }
+    out[s * stride] = v;
+  }
+}
+
+template <int L, typename T>
+static int launch_diag_LT(const u64 *bra, const T *h1e, const T *h2e, T *out, long long n, long long stride, int sorb, int nele,
+                          cudaStream_t st) {
+  const size_t smem = sizeof(T) * ((size_t)sorb * sorb + sorb);
+  if (smem <= 200 * 1024 && n >= 4096) {  // below that the table build would dominate
+    if (smem > 48 * 1024 &&
+        cudaFuncSetAttribute(diag_table_kernel<L, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+      return check_launch("diag_table_kernel smem opt-in");
+    // samples per thread: up to 4, fewer when that would leave SMs without a CTA
+    int per_thread = (int)(n / (148LL * 4 * kDiagThreads));
+    per_thread = per_thread < 1 ? 1 : (per_thread > 4 ? 4 : per_thread);
+    const long long per = (long long)kDiagThreads * per_thread;
+    diag_table_kernel<L, T><<<(unsigned)((n + per - 1) / per), kDiagThreads, smem, st>>>(bra, h1e, h2e, out, n, stride, sorb, nele,
+                                                                                       per_thread);
+    count_launch();
+    return check_launch("diag_table_kernel");
+  }
+  diag_kernel<L, T><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(bra, h1e, h2e, out, n, stride, sorb, nele);
+  count_launch();
+  return check_launch("diag_kernel");
+}
+
 // flag_bit=True companion of get_comb_tensor: states[n, M, sorb] = +-1 of every comb row
 // (cpu_tensor.cpp:186-190, excitation.cpp:171-181)
 template <int L>
@@ -365,9 +474,7 @@ static int launch_enumerate_L(const u64 *bra, const T *h1e, const T *h2e, const 
     if (int rc = check_launch("enumerate_plain_kernel")) return rc;
   }
   if (WITH_H) {
-    diag_kernel<L, T><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(bra, h1e, h2e, hmat, n, M, g.sorb, g.nele);
-    count_launch();
-    if (int rc = check_launch("diag_kernel")) return rc;
+    if (int rc = launch_diag_LT<L, T>(bra, h1e, h2e, hmat, n, M, g.sorb, g.nele, st)) return rc;
   }
   return 0;
 }
@@ -402,15 +509,13 @@ int launch_comb_hij_f32(const u64 *bra, const float *h1e, const float *h2e, cons
 int launch_diag_f64(const u64 *bra, const double *h1e, const double *h2e, double *out, long long n, long long stride, int L,
                     int sorb, int nele, cudaStream_t st) {
   if (n == 0) return 0;
-  const unsigned blocks = (unsigned)((n + 127) / 128);
   switch (L) {
-    case 1: diag_kernel<1, double><<<blocks, 128, 0, st>>>(bra, h1e, h2e, out, n, stride, sorb, nele); break;
-    case 2: diag_kernel<2, double><<<blocks, 128, 0, st>>>(bra, h1e, h2e, out, n, stride, sorb, nele); break;
-    case 3: diag_kernel<3, double><<<blocks, 128, 0, st>>>(bra, h1e, h2e, out, n, stride, sorb, nele); break;
-    default: set_error("unsupported ONV length L=%d", L); return 1;
+    case 1: return launch_diag_LT<1, double>(bra, h1e, h2e, out, n, stride, sorb, nele, st);
+    case 2: return launch_diag_LT<2, double>(bra, h1e, h2e, out, n, stride, sorb, nele, st);
+    case 3: return launch_diag_LT<3, double>(bra, h1e, h2e, out, n, stride, sorb, nele, st);
   }
-  count_launch();
-  return check_launch("diag_kernel");
+  set_error("unsupported ONV length L=%d", L);
+  return 1;
 }
 
 int launch_states(const u64 *comb, double *states, long long rows, int sorb, cudaStream_t st) {

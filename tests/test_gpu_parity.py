@@ -519,3 +519,20 @@ def test_weighted_moments_and_statistics(n, cplx):
     var = (p * np.abs(e - mean) ** 2).sum()
     for st in (energy_statistics(dev(e), dev(p)), energy_statistics_amplitudes(dev(e), dev(amp))):
         assert abs(st["mean"] - mean) < 1e-11 and abs(st["var"] - var) < 1e-11 * max(1.0, var) and st["n"] == n
+
+
+@pytest.mark.parametrize("sorb,noA,noB", [(12, 3, 3), (40, 15, 15), (100, 2, 1), (132, 3, 2)])
+def test_diagonal_from_the_shared_memory_table_is_bit_identical(sorb, noA, noB):
+    """Large batches compute H_ii from a per-CTA table of <pq||pq> in shared memory, small ones gather from
+    the packed array: same values, same order of additions -> identical bits; oracle spot check."""
+    n = 6000 if sorb != 40 else 4500
+    x = S.random_onvs(n, sorb, noA, noB, seed=50 + sorb) if sorb > 12 else np.repeat(S.random_onvs(300, sorb, noA, noB, seed=62), 20, axis=0)
+    h1e, h2e = S.random_packed_integrals(sorb, seed=51, symmetric=False)
+    dx, dh1, dh2 = dev(x), dev(h1e), dev(h2e)
+    _, big = ops.get_comb_hij_fused(dx, dh1, dh2, sorb, noA + noB, noA, noB)
+    diag_big = big[:, 0].clone()
+    del big
+    parts = [ops.get_comb_hij_fused(dx[i : i + 1000], dh1, dh2, sorb, noA + noB, noA, noB)[1][:, 0].clone() for i in range(0, n, 1000)]
+    assert torch.equal(diag_big, torch.cat(parts))
+    _, want = O.comb_hij_fused(x[:4], h1e, h2e, sorb, noA + noB, noA, noB)
+    np.testing.assert_array_equal(diag_big[:4].cpu().numpy(), want[:, 0])
