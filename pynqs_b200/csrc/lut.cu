@@ -31,10 +31,13 @@ lut_indexed_kernel(const u64 *__restrict__ key, long long N, IndexView iv, const
                    long long *__restrict__ idx, unsigned char *__restrict__ mask) {
   const bool dup = iv.hdr->has_dup != 0;  // duplicates: reproduce the reference's probe sequence instead
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
-    const Onv<L> x = load_onv<L>(q + t * L);
+    // queries and results stream through once: evict-first, so that the index stays in L2
+    Onv<L> x;
+#pragma unroll
+    for (int w = 0; w < L; ++w) x.w[w] = __ldcs(q + t * L + w);
     const long long r = dup ? classic_search<L>(key, N, x) : indexed_search<L>(key, iv, x);
-    idx[t] = r;
-    mask[t] = r >= 0;
+    __stcs(idx + t, r);
+    __stcs(mask + t, (unsigned char)(r >= 0));
   }
 }
 
