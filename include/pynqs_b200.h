@@ -125,6 +125,25 @@ int pynqs_eloc_sample_space(const uint8_t *bra, int64_t n, const double *h1e, co
                             int64_t N, const void *group_ws, void *scratch, int64_t scratch_bytes, void *eloc,
                             void *psi0, void *stream);
 
+/* ---- REDUCE method (vmc/energy/eloc.py:257-297, additive) -----------------------------------------
+ * The reference materialises comb [n, M, 8L] and Hmat [n, M] and keeps torch.where(|Hmat| >= eps).  These
+ * entry points return the kept rows only, in the same (ascending flat index s * M + m) order:
+ *   pynqs_reduce_count: offsets int64[n + 1] = exclusive prefix of the per-sample counts, offsets[n] = K;
+ *   pynqs_reduce_emit : x uint8[K, 8L] (determinants), hij T[K] (values, bit-identical to get_comb_hij_fused),
+ *                       idx int64[K] (flat indices) written at those offsets.
+ * prep_ws (pynqs_prepare_integrals) is required.  scratch: pynqs_reduce_scratch_bytes(n) bytes.
+ *   pynqs_reduce_eloc : eloc[s] = sum over kept rows of sample s of (psi_k / psi0) * hij_k, psi0 = psi of row 0
+ *                       (0 when row 0 was not kept); psi double[K] or interleaved complex128[K], hij double[K]. */
+int64_t pynqs_reduce_scratch_bytes(int64_t n);
+int pynqs_reduce_count(const uint8_t *bra, const void *h1e, const void *h2e, const void *prep_ws, int64_t n, int sorb, int nele,
+                       int noA, int noB, double eps, int dtype, void *scratch, int64_t scratch_bytes, int64_t *offsets,
+                       void *stream);
+int pynqs_reduce_emit(const uint8_t *bra, const void *h1e, const void *h2e, const void *prep_ws, int64_t n, int sorb, int nele,
+                      int noA, int noB, double eps, int dtype, void *scratch, int64_t scratch_bytes, const int64_t *offsets,
+                      uint8_t *x, void *hij, int64_t *idx, void *stream);
+int pynqs_reduce_eloc(const void *psi, int psi_complex, const double *hij, const int64_t *idx, const int64_t *offsets, int64_t n,
+                      int64_t M, void *eloc, void *psi0, void *stream);
+
 /* ---- unique-sample table: sort (utils/public_function.py:626-689, 754-788) ----------------------
  * Stable ascending sort of N keys (uint64[N, L] little-endian multi-word integers, the order of the
  * reference's torch_sort_onv) together with their psi values (psi_bytes = 8 or 16 per row; psi may

@@ -168,3 +168,29 @@ def eloc_sample_space(bra_u8, h1e, h2e, key_sorted_u8, psi_sorted, sorb, nele, n
     n, M, w = c.shape
     idx, _ = lut(key_sorted_u8, c.reshape(n * M, w))
     return eloc_rows(idx.reshape(n, M), h, psi_sorted)
+
+
+def reduced(bra_u8, h1e, h2e, sorb, nele, noA, noB, eps):
+    """REDUCE method, kept set (vmc/energy/eloc.py:257-259, 289): torch.where(|Hmat| >= eps) over the
+    row-major [n, M] matrix of the fused operator -> (x [K, 8L], hij [K], flat idx [K], offsets [n + 1])."""
+    c, h = comb_hij_fused(bra_u8, h1e, h2e, sorb, nele, noA, noB)
+    n, M, w = c.shape
+    eps_t = h.dtype.type(eps)  # torch compares in the tensor's dtype
+    keep = np.abs(h) >= eps_t
+    idx = np.nonzero(keep.reshape(-1))[0].astype(np.int64)
+    offsets = np.concatenate([[0], np.cumsum(keep.sum(1))]).astype(np.int64)
+    return c.reshape(n * M, w)[idx], h.reshape(-1)[idx], idx, offsets
+
+
+def reduce_eloc(psi_kept, hij_kept, idx, offsets, M):
+    """Last lines of _reduce_psi (eloc.py:294-307): psi scattered into zeros [n, M], eloc = sum (psi / psi[:, 0]) * Hmat."""
+    n = len(offsets) - 1
+    cplx = np.iscomplexobj(psi_kept)
+    psi = np.zeros(n * M, dtype=np.complex128 if cplx else np.float64)
+    hm = np.zeros(n * M, dtype=np.float64)
+    psi[idx] = psi_kept
+    hm[idx] = hij_kept
+    psi = psi.reshape(n, M)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        eloc = ((psi.T / psi[:, 0]).T * hm.reshape(n, M)).sum(-1)
+    return eloc, psi[:, 0].copy()

@@ -243,6 +243,76 @@ def get_comb_hij_fused(bra: Tensor, h1e: Tensor, h2e: Tensor, sorb: int, nele: i
     return comb, hmat
 
 
+def get_comb_hij_reduced(bra: Tensor, h1e: Tensor, h2e: Tensor, sorb: int, nele: int, noA: int, noB: int, eps: float,
+                         *, prepared: "PreparedIntegrals | None" = None) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    """Additive op for the REDUCE method (vmc/energy/eloc.py:257-297): what the reference obtains from
+    get_comb_tensor + get_hij_torch + torch.where(|Hmat| >= eps), without materialising [n, M] arrays.
+    Returns (x uint8 [K, 8L], hij [K], gt_eps_idx int64 [K], offsets int64 [n + 1]): the kept determinants,
+    their matrix elements (bit-identical to get_comb_hij_fused), their flat indices s * M + m in ascending
+    order (= torch.where's), and the first kept row of every sample.  One host synchronisation (K)."""
+    dev = _need_cuda(bra, h1e, h2e)
+    for t, nm in ((bra, "bra"), (h1e, "h1e"), (h2e, "h2e")):
+        _contig(t, nm)
+    if bra.dim() == 1:
+        bra = bra.view(1, -1)
+    L = _check_width(bra, sorb, "bra")
+    code = _fdtype(h1e, h2e)
+    _check_integrals(h1e, h2e, sorb)
+    get_Num_SinglesDoubles(sorb, noA, noB)  # geometry / overflow checks
+    if not (eps >= 0.0):
+        raise ValueError("eps must be >= 0")
+    n = bra.size(0)
+    offsets = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+    if n == 0:
+        return (torch.empty((0, 8 * L), dtype=torch.uint8, device=dev), torch.empty(0, dtype=h1e.dtype, device=dev),
+                torch.empty(0, dtype=torch.int64, device=dev), offsets)
+    if prepared is None:
+        prepared = _cached_prep(h2e, sorb)
+    if prepared.sorb != sorb or prepared.dtype != h2e.dtype:
+        raise ValueError("prepared integrals do not match sorb / dtype")
+    lib = _lib.load()
+    nbytes = int(lib.pynqs_reduce_scratch_bytes(i64(n)))
+    scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    common = (vp(bra.data_ptr()), vp(h1e.data_ptr()), vp(h2e.data_ptr()), vp(prepared.workspace.data_ptr()), i64(n), int(sorb),
+              int(nele), int(noA), int(noB), _lib.ctypes.c_double(float(eps)), code, vp(scratch.data_ptr()), i64(nbytes))
+    with torch.cuda.device(dev):
+        _lib.check(lib.pynqs_reduce_count(*common, vp(offsets.data_ptr()), _stream(dev)))
+        K = int(offsets[n].item())
+        x = torch.empty((K, 8 * L), dtype=torch.uint8, device=dev)
+        hij = torch.empty(K, dtype=h1e.dtype, device=dev)
+        idx = torch.empty(K, dtype=torch.int64, device=dev)
+        _lib.check(lib.pynqs_reduce_emit(*common, vp(offsets.data_ptr()), vp(x.data_ptr()), vp(hij.data_ptr()), vp(idx.data_ptr()),
+                                         _stream(dev)))
+    return x, hij, idx, offsets
+
+
+def reduce_eloc(psi: Tensor, hij: Tensor, gt_eps_idx: Tensor, offsets: Tensor, M: int) -> Tuple[Tensor, Tensor]:
+    """eloc[s] = sum over the kept rows of sample s of (psi_k / psi0) * hij_k -- the last lines of _reduce_psi
+    (eloc.py:283-297) on the compacted rows.  psi0 = psi of the sample's row 0 (0 if it was not kept, as in the
+    reference).  Returns (eloc [n], psi0 [n]) in psi's dtype (float64 or complex128)."""
+    dev = _need_cuda(psi, hij, gt_eps_idx, offsets)
+    if psi.dtype not in (torch.float64, torch.complex128):
+        raise ValueError("psi must be float64 or complex128")
+    psi = psi.contiguous()
+    hij = hij.to(torch.float64).contiguous()
+    gt_eps_idx = gt_eps_idx.contiguous()
+    offsets = offsets.contiguous()
+    if hij.numel() != psi.numel() or gt_eps_idx.numel() != psi.numel() or offsets.dtype != torch.int64 or gt_eps_idx.dtype != torch.int64:
+        raise ValueError("psi, hij and gt_eps_idx must have one entry per kept row; offsets / gt_eps_idx int64")
+    n = offsets.numel() - 1
+    eloc = torch.empty(n, dtype=psi.dtype, device=dev)
+    psi0 = torch.empty(n, dtype=psi.dtype, device=dev)
+    if n > 0:
+        with torch.cuda.device(dev):
+            _lib.check(
+                _lib.load().pynqs_reduce_eloc(
+                    vp(psi.data_ptr()), int(psi.is_complex()), vp(hij.data_ptr()), vp(gt_eps_idx.data_ptr()), vp(offsets.data_ptr()),
+                    i64(n), i64(M), vp(eloc.data_ptr()), vp(psi0.data_ptr()), _stream(dev),
+                )
+            )
+    return eloc, psi0
+
+
 def get_hij_torch(bra: Tensor, ket: Tensor, h1e: Tensor, h2e: Tensor, sorb: int, nele: int) -> Tensor:
     """<bra|H|ket> (C_extension.pyi:92-123): ket 3-D [n, m, 8L] -> local-energy layout [n, m];
     ket 2-D [m, 8L] -> matrix [n, m].  dtype/device of h1e."""

@@ -55,6 +55,12 @@ long long sort_workspace_bytes(long long);
 int launch_sort_table(const u64 *, const void *, long long, int, int, int, u64 *, void *, long long *, void *, long long, cudaStream_t);
 long long moments_scratch_bytes();
 int launch_moments(const double *, int, const double *, int, long long, void *, double *, cudaStream_t);
+long long reduce_scratch_bytes(long long);
+template <typename T>
+int launch_reduce(const u64 *, const T *, const T *, const void *, long long, const ExcGeom &, double, int, void *, long long,
+                  long long *, u64 *, T *, long long *, cudaStream_t);
+int launch_reduce_eloc(const double *, int, const double *, const long long *, const long long *, long long, long long, double *,
+                       double *, cudaStream_t);
 int launch_onv_to_tensor(const u64 *, void *, int, long long, int, cudaStream_t);
 int launch_tensor_to_onv(const unsigned char *, unsigned char *, long long, int, cudaStream_t);
 
@@ -276,6 +282,61 @@ int pynqs_eloc_sample_space(const uint8_t *bra, int64_t n, const double *h1e, co
   return launch_eloc(reinterpret_cast<const u64 *>(bra), n, h1e, h2e, reinterpret_cast<const u64 *>(key),
                      (const double *)psi, psi_complex, N, group_ws, scratch, scratch_bytes, (double *)eloc, (double *)psi0, g,
                      (cudaStream_t)stream);
+}
+
+int64_t pynqs_reduce_scratch_bytes(int64_t n) { return reduce_scratch_bytes(n); }
+
+static int reduce_common(const uint8_t *bra, const void *h1e, const void *h2e, const void *prep_ws, int64_t n, int sorb, int nele,
+                         int noA, int noB, double eps, int dtype, int emit, void *scratch, int64_t scratch_bytes, int64_t *offsets,
+                         uint8_t *x, void *hij, int64_t *idx, void *stream) {
+  if (int rc = check_geometry(sorb, nele, noA, noB)) return rc;
+  long long nsd;
+  if (int rc = num_sd_checked(sorb, noA, noB, &nsd)) return rc;
+  if (dtype != PYNQS_F32 && dtype != PYNQS_F64) {
+    set_error("reduce: dtype %d is neither float32 nor float64", dtype);
+    return PYNQS_EVALUE;
+  }
+  if (prep_ws == nullptr) {
+    set_error("reduce: the prepared integrals (pynqs_prepare_integrals) are required");
+    return PYNQS_EVALUE;
+  }
+  if (n < 0 || !(eps >= 0.0)) {
+    set_error("reduce: bad n = %lld or eps = %g", (long long)n, eps);
+    return PYNQS_EVALUE;
+  }
+  const ExcGeom g = make_geom(sorb, nele, noA, noB);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == PYNQS_F64)
+    return launch_reduce<double>(reinterpret_cast<const u64 *>(bra), (const double *)h1e, (const double *)h2e, prep_ws, n, g, eps, emit,
+                                 scratch, scratch_bytes, reinterpret_cast<long long *>(offsets), reinterpret_cast<u64 *>(x),
+                                 (double *)hij, reinterpret_cast<long long *>(idx), st);
+  return launch_reduce<float>(reinterpret_cast<const u64 *>(bra), (const float *)h1e, (const float *)h2e, prep_ws, n, g, eps, emit,
+                              scratch, scratch_bytes, reinterpret_cast<long long *>(offsets), reinterpret_cast<u64 *>(x), (float *)hij,
+                              reinterpret_cast<long long *>(idx), st);
+}
+
+int pynqs_reduce_count(const uint8_t *bra, const void *h1e, const void *h2e, const void *prep_ws, int64_t n, int sorb, int nele,
+                       int noA, int noB, double eps, int dtype, void *scratch, int64_t scratch_bytes, int64_t *offsets,
+                       void *stream) {
+  return reduce_common(bra, h1e, h2e, prep_ws, n, sorb, nele, noA, noB, eps, dtype, 0, scratch, scratch_bytes, offsets, nullptr,
+                       nullptr, nullptr, stream);
+}
+
+int pynqs_reduce_emit(const uint8_t *bra, const void *h1e, const void *h2e, const void *prep_ws, int64_t n, int sorb, int nele,
+                      int noA, int noB, double eps, int dtype, void *scratch, int64_t scratch_bytes, const int64_t *offsets,
+                      uint8_t *x, void *hij, int64_t *idx, void *stream) {
+  return reduce_common(bra, h1e, h2e, prep_ws, n, sorb, nele, noA, noB, eps, dtype, 1, scratch, scratch_bytes,
+                       const_cast<int64_t *>(offsets), x, hij, idx, stream);
+}
+
+int pynqs_reduce_eloc(const void *psi, int psi_complex, const double *hij, const int64_t *idx, const int64_t *offsets, int64_t n,
+                      int64_t M, void *eloc, void *psi0, void *stream) {
+  if (n < 0 || M <= 0) {
+    set_error("reduce_eloc: bad n = %lld or M = %lld", (long long)n, (long long)M);
+    return PYNQS_EVALUE;
+  }
+  return launch_reduce_eloc((const double *)psi, psi_complex, hij, reinterpret_cast<const long long *>(idx),
+                            reinterpret_cast<const long long *>(offsets), n, M, (double *)eloc, (double *)psi0, (cudaStream_t)stream);
 }
 
 int64_t pynqs_sort_bytes(int64_t N) { return sort_workspace_bytes(N < 0 ? 0 : N); }

@@ -124,6 +124,78 @@ constexpr int kRowsPerThread = 4;  // independent rows (and integral gathers) in
 // row m holds excitation r = m - 1.  A warp takes chunks of 32 * ROWS consecutive rows; lane l
 // owns rows chunk + l + 32 j, so each store instruction of the warp covers 32 consecutive rows
 // (256 contiguous bytes of comb at L = 1 and of Hmat): coalesced, every byte written once.
+// The ROWS rows  c + lane + 32 j  (j < ROWS) of one excitation class (CLS: 0/1 single a/b, 2/3 double aa/bb,
+// 4 double ab; row m holds excitation r = m - 1): determinant, |value| and sign word of each; rows >= hi are
+// left as (x, 0, 0).
+template <int L, typename T, bool WITH_H, int CLS, int ROWS>
+__device__ __forceinline__ void class_rows(const Onv<L> &x, const EnumEntry<L> *__restrict__ tab, const TableOffsets &to,
+                                           const ExcGeom &g, const OrbLists &lists, const T *__restrict__ h1e,
+                                           const PrepView<T> &prep, int c, int hi, Onv<L> (&row)[ROWS], T (&val)[ROWS],
+                                           u32 (&sgn)[ROWS]) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int j = 0; j < ROWS; ++j) {
+    const int m = c + lane + 32 * j;
+    row[j] = x;
+    val[j] = (T)0.0;
+    sgn[j] = 0;
+    if (m < hi) {
+      const u32 r = (u32)(m - 1);
+      if (CLS <= 1) {
+        const EnumEntry<L> e1 = load_entry<L>(tab + (CLS == 0 ? to.sa + (int)r : to.sb + (int)(r - g.d0)));
+        row[j] = entry_apply<L>(x, e1);
+        if (WITH_H) {
+          // single h -> p: h1e(h,p) + sum over occupied k, in the reference's order, of <hk||pk>
+          // SA packs hA | pA << 16, SB packs pB | hB << 16
+          const u32 h = CLS == 0 ? (e1.cmp & 0xffu) : (e1.cmp >> 16), p = CLS == 0 ? (e1.cmp >> 16) : (e1.cmp & 0xffu);
+          const u32 na = (u32)prep.na;
+          const size_t kstride = (size_t)2 * na * na;
+          const int n_occ = lists.n_occ;
+          T v = (T)0.0;
+          v += __ldg(h1e + (size_t)p * g.sorb + h);
+          const T *line = prep.s + ((size_t)(h & 1u) * na + (p >> 1)) * na + (h >> 1);
+          for (int q = 0; q < n_occ; q += 4) {
+            T t[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) t[i] = (q + i < n_occ) ? __ldg(line + kstride * lists.occ_order[q + i]) : (T)0.0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              if (q + i < n_occ) v += t[i];
+          }
+          val[j] = v;
+          sgn[j] = e1.off;  // bit 31 = the single's sign
+        }
+      } else {
+        int t1, t2;
+        if (CLS == 4) {
+          const u32 q = r - (u32)g.d3;
+          const u32 jb = fdiv(q, g.by_sA);
+          t1 = to.sa + (int)(q - jb * g.sA);
+          t2 = to.sb + (int)jb;
+        } else if (CLS == 2) {
+          t1 = to.hpa + (int)(r - fdiv(r, g.by_noAA) * g.noAA);  // r % noAA with the GLOBAL r (quirk Q1)
+          t2 = to.ppa + (int)fdiv(r - (u32)g.d1, g.by_noAA);
+        } else {
+          t1 = to.hpb + (int)(r - fdiv(r, g.by_noBB) * g.noBB);
+          t2 = to.ppb + (int)fdiv(r - (u32)g.d2, g.by_noBB);
+        }
+        const EnumEntry<L> e1 = load_entry<L>(tab + t1);
+        const EnumEntry<L> e2 = load_entry<L>(tab + t2);
+        row[j] = entry_apply<L>(entry_apply<L>(x, e1), e2);
+        if (WITH_H) {
+          const HitInfo i1 = {e1.off, e1.cmp}, i2 = {e2.off, e2.cmp};
+          const T *tbl = CLS == 4 ? prep.ab : (CLS == 2 ? prep.aa : prep.bb);
+          val[j] = __ldg(tbl + ((i1.off + i2.off) & 0x7fffffffu));
+          sgn[j] = double_sign_word(CLS == 4, i1, i2);
+        }
+      }
+    }
+  }
+}
+
+// Rows [lo, hi) of one excitation class.  A warp takes chunks of 32 * ROWS consecutive rows; lane l owns rows
+// chunk + l + 32 j, so each store instruction of the warp covers 32 consecutive rows (256 contiguous bytes of
+// comb at L = 1 and of Hmat): coalesced, every byte written once.
 template <int L, typename T, bool WITH_H, int CLS, int ROWS>
 __device__ __forceinline__ void enumerate_class(const Onv<L> &x, const EnumEntry<L> *__restrict__ tab, const TableOffsets &to,
                                                 const ExcGeom &g, const OrbLists &lists, const T *__restrict__ h1e,
@@ -135,64 +207,7 @@ __device__ __forceinline__ void enumerate_class(const Onv<L> &x, const EnumEntry
     Onv<L> row[ROWS];
     T val[ROWS];
     u32 sgn[ROWS];
-#pragma unroll
-    for (int j = 0; j < ROWS; ++j) {
-      const int m = c + lane + 32 * j;
-      row[j] = x;
-      val[j] = (T)0.0;
-      sgn[j] = 0;
-      if (m < hi) {
-        const u32 r = (u32)(m - 1);
-        if (CLS <= 1) {
-          const EnumEntry<L> e1 = load_entry<L>(tab + (CLS == 0 ? to.sa + (int)r : to.sb + (int)(r - g.d0)));
-          row[j] = entry_apply<L>(x, e1);
-          if (WITH_H) {
-            // single h -> p: h1e(h,p) + sum over occupied k, in the reference's order, of <hk||pk>
-            // SA packs hA | pA << 16, SB packs pB | hB << 16
-            const u32 h = CLS == 0 ? (e1.cmp & 0xffu) : (e1.cmp >> 16), p = CLS == 0 ? (e1.cmp >> 16) : (e1.cmp & 0xffu);
-            const u32 na = (u32)prep.na;
-            const size_t kstride = (size_t)2 * na * na;
-            const int n_occ = lists.n_occ;
-            T v = (T)0.0;
-            v += __ldg(h1e + (size_t)p * g.sorb + h);
-            const T *line = prep.s + ((size_t)(h & 1u) * na + (p >> 1)) * na + (h >> 1);
-            for (int q = 0; q < n_occ; q += 4) {
-              T t[4];
-#pragma unroll
-              for (int i = 0; i < 4; ++i) t[i] = (q + i < n_occ) ? __ldg(line + kstride * lists.occ_order[q + i]) : (T)0.0;
-#pragma unroll
-              for (int i = 0; i < 4; ++i)
-                if (q + i < n_occ) v += t[i];
-            }
-            val[j] = v;
-            sgn[j] = e1.off;  // bit 31 = the single's sign
-          }
-        } else {
-          int t1, t2;
-          if (CLS == 4) {
-            const u32 q = r - (u32)g.d3;
-            const u32 jb = fdiv(q, g.by_sA);
-            t1 = to.sa + (int)(q - jb * g.sA);
-            t2 = to.sb + (int)jb;
-          } else if (CLS == 2) {
-            t1 = to.hpa + (int)(r - fdiv(r, g.by_noAA) * g.noAA);  // r % noAA with the GLOBAL r (quirk Q1)
-            t2 = to.ppa + (int)fdiv(r - (u32)g.d1, g.by_noAA);
-          } else {
-            t1 = to.hpb + (int)(r - fdiv(r, g.by_noBB) * g.noBB);
-            t2 = to.ppb + (int)fdiv(r - (u32)g.d2, g.by_noBB);
-          }
-          const EnumEntry<L> e1 = load_entry<L>(tab + t1);
-          const EnumEntry<L> e2 = load_entry<L>(tab + t2);
-          row[j] = entry_apply<L>(entry_apply<L>(x, e1), e2);
-          if (WITH_H) {
-            const HitInfo i1 = {e1.off, e1.cmp}, i2 = {e2.off, e2.cmp};
-            const T *tbl = CLS == 4 ? prep.ab : (CLS == 2 ? prep.aa : prep.bb);
-            val[j] = __ldg(tbl + ((i1.off + i2.off) & 0x7fffffffu));
-            sgn[j] = double_sign_word(CLS == 4, i1, i2);
-          }
-        }
-      }
-    }
+    class_rows<L, T, WITH_H, CLS, ROWS>(x, tab, to, g, lists, h1e, prep, c, hi, row, val, sgn);
 #pragma unroll
     for (int j = 0; j < ROWS; ++j) {
       const int m = c + lane + 32 * j;
@@ -530,6 +545,279 @@ int launch_states(const u64 *comb, double *states, long long rows, int sorb, cud
   }
   count_launch();
   return check_launch("states_kernel");
+}
+
+// ---- REDUCE method: only the connected determinants with |<x|H|x'>| >= eps ----------------------------------
+// The reference materialises comb [n, M, 8L] and Hmat [n, M], then keeps torch.where(|Hmat| >= eps)
+// (vmc/energy/eloc.py:257-297).  Here nothing of size [n, M] is written: a counting pass, an exclusive scan,
+// and an emitting pass that recomputes the rows and writes the kept ones -- determinant, value and flat index
+// s * M + m -- in exactly torch.where's order (ascending flat index).  One CTA per sample; inside a CTA the
+// rows go through in chunks of 8 warps x 32 ROWS, and the kept rows of a chunk are ranked with ballots
+// (inside a warp) and a prefix over the warps' counts (shared memory), so the order does not depend on timing.
+template <int L, typename T, int CLS, int ROWS, bool EMIT>
+__device__ __forceinline__ void reduce_class(const Onv<L> &x, const EnumEntry<L> *__restrict__ tab, const TableOffsets &to,
+                                             const ExcGeom &g, const OrbLists &lists, const T *__restrict__ h1e,
+                                             const PrepView<T> &prep, int lo, int hi, T eps, u32 &kept, u32 *warp_cnt,
+                                             long long out_base, long long flat_base, u64 *__restrict__ x_out,
+                                             T *__restrict__ h_out, long long *__restrict__ idx_out) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int kChunk = 32 * ROWS, kWarps = kEnumThreads / 32;
+  for (int c0 = lo; c0 < hi; c0 += kWarps * kChunk) {  // same trip count for every warp: there are barriers inside
+    const int c = c0 + warp * kChunk;
+    Onv<L> row[ROWS];
+    T val[ROWS];
+    u32 sgn[ROWS];
+    class_rows<L, T, true, CLS, ROWS>(x, tab, to, g, lists, h1e, prep, c, hi, row, val, sgn);
+    u32 bal[ROWS], wc = 0;
+#pragma unroll
+    for (int j = 0; j < ROWS; ++j) {
+      const int m = c + lane + 32 * j;
+      bal[j] = __ballot_sync(0xffffffffu, m < hi && fabs(val[j]) >= eps);
+      wc += (u32)__popc(bal[j]);
+    }
+    if (!EMIT) {
+      kept += wc;  // per-warp tally, summed at the end
+      continue;
+    }
+    if (lane == 0) warp_cnt[warp] = wc;
+    __syncthreads();
+    u32 before = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) {
+      const u32 t = warp_cnt[w];
+      before += w < warp ? t : 0u;
+      total += t;
+    }
+    u32 pos = kept + before;
+#pragma unroll
+    for (int j = 0; j < ROWS; ++j) {
+      if ((bal[j] >> lane) & 1u) {
+        const long long o = out_base + pos + (u32)__popc(bal[j] & ((1u << lane) - 1u));
+        store_row<L>(x_out + o * L, row[j]);
+        h_out[o] = flip_sign((T)1.0 * val[j], sgn[j]);
+        idx_out[o] = flat_base + (c + lane + 32 * j);
+      }
+      pos += (u32)__popc(bal[j]);
+    }
+    kept += total;
+    __syncthreads();
+  }
+}
+
+template <int L, typename T, bool EMIT>
+__global__ void __launch_bounds__(kEnumThreads)
+reduce_kernel(const u64 *__restrict__ bra, const T *__restrict__ h1e, PrepView<T> prep, const T *__restrict__ diag, T eps,
+              long long *__restrict__ offsets, u64 *__restrict__ x_out, T *__restrict__ h_out, long long *__restrict__ idx_out,
+              long long n, ExcGeom g) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  OrbLists &lists = *reinterpret_cast<OrbLists *>(smem_raw);
+  EnumEntry<L> *tab = reinterpret_cast<EnumEntry<L> *>(smem_raw + sizeof(OrbLists));
+  __shared__ u32 warp_cnt[kEnumThreads / 32];
+  __shared__ unsigned long long s_total;
+  const long long s = blockIdx.x;
+  if (s >= n) return;
+  const Onv<L> x = load_onv<L>(bra + s * L);
+  if (threadIdx.x < 32) build_lists<L>(x, g.sorb, g.noA, g.noB, lists, threadIdx.x);
+  if (threadIdx.x == 0) s_total = 0ull;
+  __syncthreads();
+  const TableOffsets to = table_offsets(g);
+  const u32 na = (u32)prep.na, npair = (u32)prep.npair;
+  for_each_table_entry(g, lists, to, [&](int t, int kind, u32 e0, u32 e1) {
+    EnumEntry<L> e;
+    const HitInfo hi = make_hit_info(kind, e0, e1, na, npair);
+    e.off = hi.off;
+    e.cmp = hi.cmp;
+    set_mask<L>(e, e0 & 0xffu, e1 & 0xffu);
+    tab[t] = e;
+  });
+  __syncthreads();
+
+  const long long M = (long long)g.nsd + 1;
+  const long long out_base = EMIT ? offsets[s] : 0, flat_base = s * M;
+  // row 0: the sample itself with <x|H|x>
+  const T hii = diag[s];
+  const bool keep0 = fabs(hii) >= eps;
+  u32 kept = 0;
+  if (EMIT) {
+    kept = keep0 ? 1u : 0u;  // uniform running count of the CTA
+    if (keep0 && threadIdx.x == 0) {
+      store_row<L>(x_out + out_base * L, x);
+      h_out[out_base] = hii;
+      idx_out[out_base] = flat_base;
+    }
+  } else if (threadIdx.x == 0 && keep0) {
+    kept = 1u;  // tallies are per warp (lane-uniform); warp 0 carries row 0
+  }
+  if (!EMIT) kept = __shfl_sync(0xffffffffu, kept, 0);
+  const int Mi = (int)M;
+  reduce_class<L, T, 0, 1, EMIT>(x, tab, to, g, lists, h1e, prep, 1, g.d0 + 1, eps, kept, warp_cnt, out_base, flat_base, x_out, h_out, idx_out);
+  reduce_class<L, T, 1, 1, EMIT>(x, tab, to, g, lists, h1e, prep, g.d0 + 1, g.d1 + 1, eps, kept, warp_cnt, out_base, flat_base, x_out, h_out, idx_out);
+  reduce_class<L, T, 2, kRowsPerThread, EMIT>(x, tab, to, g, lists, h1e, prep, g.d1 + 1, g.d2 + 1, eps, kept, warp_cnt, out_base, flat_base, x_out, h_out, idx_out);
+  reduce_class<L, T, 3, kRowsPerThread, EMIT>(x, tab, to, g, lists, h1e, prep, g.d2 + 1, g.d3 + 1, eps, kept, warp_cnt, out_base, flat_base, x_out, h_out, idx_out);
+  reduce_class<L, T, 4, kRowsPerThread, EMIT>(x, tab, to, g, lists, h1e, prep, g.d3 + 1, Mi, eps, kept, warp_cnt, out_base, flat_base, x_out, h_out, idx_out);
+  if (!EMIT) {
+    if ((threadIdx.x & 31) == 0) atomicAdd(&s_total, (unsigned long long)kept);
+    __syncthreads();
+    if (threadIdx.x == 0) offsets[s] = (long long)s_total;  // counts; the scan turns them into offsets
+  }
+}
+
+}  // namespace pynqs
+
+#include <cub/device/device_scan.cuh>
+
+namespace pynqs {
+
+struct ReduceScratch {
+  long long diag, cub, total;
+  size_t cub_bytes;
+};
+
+static ReduceScratch reduce_scratch_layout(long long n) {
+  ReduceScratch l;
+  size_t tmp = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tmp, (const long long *)nullptr, (long long *)nullptr, (int)(n + 1));
+  l.diag = 0;
+  l.cub = (8 * n + 255) / 256 * 256 + 256;
+  l.cub_bytes = tmp;
+  l.total = l.cub + (long long)tmp + 256;
+  return l;
+}
+
+long long reduce_scratch_bytes(long long n) { return reduce_scratch_layout(n < 0 ? 0 : n).total; }
+
+template <int L, typename T, bool EMIT>
+static int launch_reduce_LT(const u64 *bra, const T *h1e, const T *h2e, const void *prep_ws, long long n, const ExcGeom &g, double eps,
+                            void *scratch, long long *offsets, u64 *x_out, T *h_out, long long *idx_out, cudaStream_t st) {
+  const ReduceScratch lay = reduce_scratch_layout(n);
+  char *sc = static_cast<char *>(scratch);
+  T *diag = reinterpret_cast<T *>(sc + lay.diag);
+  if (int rc = launch_diag_LT<L, T>(bra, h1e, h2e, diag, n, 1, g.sorb, g.nele, st)) return rc;
+  const size_t smem = sizeof(OrbLists) + sizeof(EnumEntry<L>) * (size_t)table_offsets(g).total;
+  auto kern = reduce_kernel<L, T, EMIT>;
+  if (smem > 48 * 1024 && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    return check_launch("reduce_kernel smem opt-in");
+  const PrepView<T> pv = prep_view<T>(prep_ws, g.sorb);
+  kern<<<(unsigned)n, kEnumThreads, smem, st>>>(bra, h1e, pv, diag, (T)eps, offsets, x_out, h_out, idx_out, n, g);
+  count_launch();
+  if (int rc = check_launch("reduce_kernel")) return rc;
+  if (!EMIT) {
+    if (cudaMemsetAsync(offsets + n, 0, 8, st) != cudaSuccess) return check_launch("reduce offsets memset");
+    size_t tmp = lay.cub_bytes;
+    const cudaError_t e = cub::DeviceScan::ExclusiveSum(sc + lay.cub, tmp, offsets, offsets, (int)(n + 1), st);
+    if (e != cudaSuccess) {
+      set_error("reduce scan: CUDA error %d (%s)", (int)e, cudaGetErrorString(e));
+      return 3;
+    }
+    count_launch(2);
+  }
+  return 0;
+}
+
+// emit = 0: offsets[n + 1] <- exclusive prefix of the per-sample counts (offsets[n] = number of kept rows);
+// emit = 1: the kept rows at those offsets
+template <typename T>
+int launch_reduce(const u64 *bra, const T *h1e, const T *h2e, const void *prep_ws, long long n, const ExcGeom &g, double eps, int emit,
+                  void *scratch, long long scratch_bytes, long long *offsets, u64 *x_out, T *h_out, long long *idx_out,
+                  cudaStream_t st) {
+  if (n == 0) return 0;
+  if (n > 0x7fffffffLL - 1) {
+    set_error("reduce: at most 2^31 - 2 samples per call (got %lld)", n);
+    return 1;
+  }
+  if (scratch_bytes < reduce_scratch_layout(n).total) {
+    set_error("reduce scratch too small: %lld < %lld bytes", scratch_bytes, reduce_scratch_layout(n).total);
+    return 4;
+  }
+#define PYNQS_REDUCE_CASE(LL)                                                                                                     \
+  case LL:                                                                                                                        \
+    return emit ? launch_reduce_LT<LL, T, true>(bra, h1e, h2e, prep_ws, n, g, eps, scratch, offsets, x_out, h_out, idx_out, st)   \
+                : launch_reduce_LT<LL, T, false>(bra, h1e, h2e, prep_ws, n, g, eps, scratch, offsets, x_out, h_out, idx_out, st);
+  switch (g.L) {
+    PYNQS_REDUCE_CASE(1)
+    PYNQS_REDUCE_CASE(2)
+    PYNQS_REDUCE_CASE(3)
+  }
+#undef PYNQS_REDUCE_CASE
+  set_error("unsupported ONV length L=%d", g.L);
+  return 1;
+}
+
+template int launch_reduce<double>(const u64 *, const double *, const double *, const void *, long long, const ExcGeom &, double, int,
+                                   void *, long long, long long *, u64 *, double *, long long *, cudaStream_t);
+template int launch_reduce<float>(const u64 *, const float *, const float *, const void *, long long, const ExcGeom &, double, int,
+                                  void *, long long, long long *, u64 *, float *, long long *, cudaStream_t);
+
+// eloc[s] = sum over the kept rows of sample s of (psi_k / psi0) * H_k, psi0 = psi of row 0 (0 when row 0 was not
+// kept, as in the reference, where psi_x1[..., 0] then stays 0).  One warp per sample, fixed order.
+template <bool CPLX>
+__global__ void __launch_bounds__(128)
+reduce_eloc_kernel(const double *__restrict__ psi, const double *__restrict__ hij, const long long *__restrict__ idx,
+                   const long long *__restrict__ offsets, long long n, long long M, double *__restrict__ eloc,
+                   double *__restrict__ psi0_out) {
+  const int lane = threadIdx.x & 31;
+  const long long s = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (s >= n) return;
+  const long long b = offsets[s], e = offsets[s + 1];
+  double p0r = 0.0, p0i = 0.0;
+  if (b < e && idx[b] == s * M) {
+    p0r = CPLX ? psi[2 * b] : psi[b];
+    p0i = CPLX ? psi[2 * b + 1] : 0.0;
+  }
+  double ar = 0.0, ai = 0.0;
+  for (long long k = b + lane; k < e; k += 32) {
+    const double h = hij[k];
+    if (CPLX) {
+      // numpy / c10 complex division (same formula as the one-pass kernels)
+      const double a = psi[2 * k], bb = psi[2 * k + 1], c = p0r, d = p0i;
+      const double ac = fabs(c), ad = fabs(d);
+      double qr, qi;
+      if (ac >= ad) {
+        if (ac == 0.0 && ad == 0.0) {
+          qr = a / ac;
+          qi = bb / ad;
+        } else {
+          const double rat = d / c, scl = 1.0 / (c + d * rat);
+          qr = (a + bb * rat) * scl;
+          qi = (bb - a * rat) * scl;
+        }
+      } else {
+        const double rat = c / d, scl = 1.0 / (d + c * rat);
+        qr = (a * rat + bb) * scl;
+        qi = (bb * rat - a) * scl;
+      }
+      ar += qr * h;
+      ai += qi * h;
+    } else {
+      ar += (psi[k] / p0r) * h;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ar += __shfl_xor_sync(0xffffffffu, ar, o);
+    if (CPLX) ai += __shfl_xor_sync(0xffffffffu, ai, o);
+  }
+  if (lane == 0) {
+    if (CPLX) {
+      eloc[2 * s] = ar;
+      eloc[2 * s + 1] = ai;
+      psi0_out[2 * s] = p0r;
+      psi0_out[2 * s + 1] = p0i;
+    } else {
+      eloc[s] = ar;
+      psi0_out[s] = p0r;
+    }
+  }
+}
+
+int launch_reduce_eloc(const double *psi, int cplx, const double *hij, const long long *idx, const long long *offsets, long long n,
+                       long long M, double *eloc, double *psi0, cudaStream_t st) {
+  if (n == 0) return 0;
+  const unsigned blocks = (unsigned)((n + 3) / 4);
+  if (cplx) reduce_eloc_kernel<true><<<blocks, 128, 0, st>>>(psi, hij, idx, offsets, n, M, eloc, psi0);
+  else reduce_eloc_kernel<false><<<blocks, 128, 0, st>>>(psi, hij, idx, offsets, n, M, eloc, psi0);
+  count_launch();
+  return check_launch("reduce_eloc_kernel");
 }
 
 }  // namespace pynqs

@@ -1,8 +1,10 @@
 """Sample-space local energy (ElocMethod.SAMPLE_SPACE, vmc/energy/eloc.py:326-397) on the new ops.
 
-Two routes with identical results:
-  * `local_energy_sample_space`  -- one fused kernel (enumerate -> hash probe -> H_ij on hits ->
-    reduce); nothing of size [n, M] is materialised, so 10^6 samples are a single launch;
+`local_energy_reduced` is the REDUCE method (eloc.py:257-297) on compacted rows.
+
+Two sample-space routes with identical results:
+  * `local_energy_sample_space`  -- the one-pass kernels (scan of the string-grouped table copies -> H_ij on
+    the hits -> reduce); nothing of size [n, M] is materialised, so 10^6 samples are a single call;
   * `local_energy_three_call`    -- the reference's sequence get_comb_hij_fused ->
     WavefunctionLUT.lookup -> scatter/divide/multiply/sum, chunked like vmc/energy/etot.py:76-146,
     kept so the unchanged reference Python keeps working on the new operators.
@@ -43,4 +45,33 @@ def local_energy_three_call(x: Tensor, h1e: Tensor, h2e: Tensor, WF_LUT: Wavefun
         comb_hij = comb_hij.to(real)
         eloc[b : b + batch] = ((psi_x1.T / psi_x1[..., 0]).T * comb_hij).sum(-1)
         psi_x[b : b + batch] = psi_x1[..., 0]
+    return eloc.to(dtype), torch.zeros_like(eloc).to(dtype), psi_x.to(dtype)
+
+
+def local_energy_reduced(x: Tensor, h1e: Tensor, h2e: Tensor, psi_of, sorb: int, nele: int, noa: int, nob: int,
+                         dtype=torch.double, eps: float = 1.0e-12, batch: int = 65536) -> Tuple[Tensor, Tensor, Tensor]:
+    """ElocMethod.REDUCE, deterministic branch (eps > 0, eps_sample = 0; eloc.py:257-297): only the connected
+    determinants with |<x|H|x'>| >= eps enter E_loc.  `psi_of(x_kept uint8 [K, 8L]) -> Tensor [K]` supplies the
+    amplitudes (the reference's Func(ansatz, x, WF_LUT, use_unique)); a WavefunctionLUT may be passed instead,
+    absent determinants then count as 0.  Returns (eloc, sloc, psi_x) like _reduce_psi."""
+    M = ops.get_Num_SinglesDoubles(sorb, noa, nob) + 1
+    if isinstance(psi_of, WavefunctionLUT):
+        lut = psi_of
+
+        def psi_of(xk: Tensor) -> Tensor:  # noqa: F811
+            found, _, value = lut.lookup(xk)
+            out = torch.zeros(xk.size(0), dtype=lut.dtype, device=xk.device)
+            out[found] = value
+            return out
+
+    elocs, psis = [], []
+    for b in range(0, x.size(0), batch):
+        xk, hij, idx, offsets = ops.get_comb_hij_reduced(x[b : b + batch], h1e, h2e, sorb, nele, noa, nob, eps)
+        psi = psi_of(xk)
+        psi = psi.to(torch.complex128 if psi.is_complex() else torch.float64)
+        e, p0 = ops.reduce_eloc(psi, hij, idx, offsets, M)
+        elocs.append(e)
+        psis.append(p0)
+    eloc = torch.cat(elocs) if elocs else torch.empty(0, dtype=dtype, device=x.device)
+    psi_x = torch.cat(psis) if psis else torch.empty(0, dtype=dtype, device=x.device)
     return eloc.to(dtype), torch.zeros_like(eloc).to(dtype), psi_x.to(dtype)

@@ -141,5 +141,68 @@ def main():
     save("eloc_c1_fullspace", eloc=eloc.numpy(), psi_x=psi_x.numpy())
 
 
+def toy_amplitude(states: torch.Tensor, sorb: int, cplx: bool) -> torch.Tensor:
+    """A deterministic stand-in for the ansatz of the REDUCE goldens: psi(x) from the +-1 occupation tensor.
+    (tests/util.py holds the same function for the test side.)"""
+    g = torch.Generator().manual_seed(77)
+    w = torch.randn(sorb, 2, generator=g, dtype=torch.float64)
+    z = states.to(torch.float64) @ w
+    amp = 0.3 + torch.tanh(0.11 * z[:, 0]) ** 2
+    return amp * torch.exp(1j * 0.7 * z[:, 1]) if cplx else amp * torch.sign(torch.cos(0.9 * z[:, 1]))
+
+
+def main_reduce():
+    """REDUCE-method goldens (vmc.energy.eloc._reduce_psi of the reference, eps > 0, eps_sample = 0) on the Fe2S2
+    integrals: ansatz only, and ansatz + WavefunctionLUT; plus the kept set (torch.where(|H| >= eps)) itself."""
+    torch.set_num_threads(os.cpu_count())
+    ref = load_ref(1)
+    libs = types.ModuleType("libs")
+    libs.__path__ = []
+    sys.modules["libs"] = libs
+    sys.modules["libs.C_extension"] = ref
+    libs.C_extension = ref
+    sys.path.insert(0, REFERENCE)
+    from utils.public_function import WavefunctionLUT  # reference code
+    from vmc.energy.eloc import _reduce_psi  # reference code
+
+    d = torch.load(os.path.join(REFERENCE, "example/Fe2S2/fe2s2-OO.pth"), weights_only=False)
+    h1e, h2e = d["h1e"], d["h2e"]
+    ci = d["ci_space"].numpy()
+    sorb, noA, noB, nele = int(d["sorb"]), int(d["noa"]), int(d["nob"]), int(d["nele"])
+    first, n, eps = 2000, 24, 1.0e-3
+    x = t(ci[first : first + n].copy())
+    comb = ref.get_comb_tensor(x, sorb, nele, noA, noB, False)[0]
+    hij = ref.get_hij_torch(x, comb, h1e, h2e, sorb, nele)
+    idx = torch.where(hij.reshape(-1).abs() >= eps)[0]
+    out = dict(first=first, n=n, eps=eps, K=int(idx.numel()), idx_sha=sha(idx.numpy()),
+               hij_sha=sha(hij.reshape(-1)[idx].numpy()), x_sha=sha(comb.reshape(-1, comb.size(2))[idx].numpy()),
+               idx_head=idx.numpy()[:64], counts=(hij.abs() >= eps).sum(1).numpy())
+    for tag, cplx in (("real", False), ("complex", True)):
+        dtype = torch.complex128 if cplx else torch.double
+
+        def ansatz(states):
+            return toy_amplitude(states, sorb, cplx)
+
+        def batcher(x, func):
+            return func(ref.onv_to_tensor(x, sorb)).to(dtype)
+
+        eloc, _, psi_x, _ = _reduce_psi(x, h1e, h2e, ansatz, batcher, sorb, nele, noA, noB, dtype=dtype, WF_LUT=None,
+                                        use_unique=True, eps=eps, eps_sample=0)
+        out[f"eloc_{tag}"] = eloc.numpy()
+        out[f"psi_x_{tag}"] = psi_x.numpy()
+        # with a LUT over half of the CI space (values differ from the ansatz on purpose)
+        psi_tab = S.random_psi(ci.shape[0] // 2, seed=43, complex_=cplx)
+        lut = WavefunctionLUT(t(ci[::2].copy()), t(psi_tab).to(dtype), sorb, "cpu")
+        eloc, _, psi_x, _ = _reduce_psi(x, h1e, h2e, ansatz, batcher, sorb, nele, noA, noB, dtype=dtype, WF_LUT=lut,
+                                        use_unique=True, eps=eps, eps_sample=0)
+        out[f"eloc_lut_{tag}"] = eloc.numpy()
+        out[f"psi_x_lut_{tag}"] = psi_x.numpy()
+    save("reduce_fe2s2", **out)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "reduce":
+        main_reduce()
+    else:
+        main()
+        main_reduce()

@@ -536,3 +536,69 @@ def test_diagonal_from_the_shared_memory_table_is_bit_identical(sorb, noA, noB):
     assert torch.equal(diag_big, torch.cat(parts))
     _, want = O.comb_hij_fused(x[:4], h1e, h2e, sorb, noA + noB, noA, noB)
     np.testing.assert_array_equal(diag_big[:4].cpu().numpy(), want[:, 0])
+
+
+# ---- REDUCE method: compacted connected determinants --------------------------------------------------------
+@pytest.mark.parametrize("tag,cplx", [("real", False), ("complex", True)])
+def test_reduce_method_matches_reference_python(tag, cplx):
+    """get_comb_hij_reduced == the reference's torch.where(|H| >= eps) set (digests: bit-exact indices, values,
+    determinants) and local_energy_reduced == vmc.energy.eloc._reduce_psi with the toy ansatz, with and without LUT."""
+    from pynqs_b200.energy import local_energy_reduced
+    from util import toy_amplitude
+
+    f = fe2s2()
+    g = load("reduce_fe2s2")
+    first, n, eps = int(g["first"]), int(g["n"]), float(g["eps"])
+    sorb, nele, noA, noB = f["sorb"], f["nele"], f["noA"], f["noB"]
+    x, h1e, h2e = dev(f["ci"][first : first + n]), dev(f["h1e"]), dev(f["h2e"])
+    xk, hk, idx, offsets = ops.get_comb_hij_reduced(x, h1e, h2e, sorb, nele, noA, noB, eps)
+    assert idx.numel() == int(g["K"]) and int(offsets[-1]) == int(g["K"])
+    assert sha(idx.cpu().numpy()) == str(g["idx_sha"]) and sha(hk.cpu().numpy()) == str(g["hij_sha"]) and sha(xk.cpu().numpy()) == str(g["x_sha"])
+    np.testing.assert_array_equal(torch.diff(offsets).cpu().numpy(), g["counts"])
+    dtype = torch.complex128 if cplx else torch.double
+
+    def ansatz(xq):
+        return toy_amplitude(ops.onv_to_tensor(xq, sorb), sorb, cplx)
+
+    eloc, _, psi_x = local_energy_reduced(x, h1e, h2e, ansatz, sorb, nele, noA, noB, dtype, eps=eps, batch=10)
+    np.testing.assert_allclose(eloc.cpu().numpy(), g[f"eloc_{tag}"], rtol=1e-12, atol=0)
+    np.testing.assert_allclose(psi_x.cpu().numpy(), g[f"psi_x_{tag}"], rtol=1e-14, atol=0)
+    keys = f["ci"][::2]
+    lut = WavefunctionLUT(dev(keys), dev(S.random_psi(keys.shape[0], seed=43, complex_=cplx)), sorb, DEV, rank=0, world_size=1)
+
+    def with_lut(xq):  # the reference's Func(ansatz, x, WF_LUT): table values where found, ansatz elsewhere
+        found, missing, value = lut.lookup(xq)
+        out = torch.empty(xq.size(0), dtype=dtype, device=xq.device)
+        out[found] = value
+        out[missing] = ansatz(xq[missing]).to(dtype)
+        return out
+
+    eloc, _, psi_x = local_energy_reduced(x, h1e, h2e, with_lut, sorb, nele, noA, noB, dtype, eps=eps)
+    np.testing.assert_allclose(eloc.cpu().numpy(), g[f"eloc_lut_{tag}"], rtol=1e-12, atol=0)
+    np.testing.assert_allclose(psi_x.cpu().numpy(), g[f"psi_x_lut_{tag}"], rtol=1e-14, atol=0)
+
+
+@pytest.mark.parametrize("name", OPS_CASES)
+def test_reduced_rows_against_oracle_and_fused(name):
+    """Every operator golden shape (L = 1, 2, 3; float32 and float64): the kept rows equal the oracle's at several
+    thresholds, eps = 0 returns the whole fused output in order, a huge eps returns nothing."""
+    c = ops_inputs(name)
+    sorb, nele, noA, noB = c["sorb"], c["nele"], c["noA"], c["noB"]
+    x, h1e, h2e = dev(c["bra"]), dev(c["h1e"]), dev(c["h2e"])
+    comb, hmat = ops.get_comb_hij_fused(x, h1e, h2e, sorb, nele, noA, noB)
+    xk, hk, idx, off = ops.get_comb_hij_reduced(x, h1e, h2e, sorb, nele, noA, noB, 0.0)
+    assert torch.equal(xk, comb.view(-1, comb.size(2))) and torch.equal(hk, hmat.view(-1))
+    assert torch.equal(idx, torch.arange(hmat.numel(), device=DEV))
+    absh = np.abs(hmat.cpu().numpy().ravel())
+    for q in (0.5, 0.97):
+        eps = float(np.quantile(absh[absh > 0], q))
+        xk, hk, idx, off = ops.get_comb_hij_reduced(x, h1e, h2e, sorb, nele, noA, noB, eps)
+        wx, wh, wi, wo = O.reduced(c["bra"], c["h1e"], c["h2e"], sorb, nele, noA, noB, eps)
+        np.testing.assert_array_equal(idx.cpu().numpy(), wi)
+        np.testing.assert_array_equal(hk.cpu().numpy(), wh)
+        np.testing.assert_array_equal(xk.cpu().numpy(), wx)
+        np.testing.assert_array_equal(off.cpu().numpy(), wo)
+    xk, hk, idx, off = ops.get_comb_hij_reduced(x, h1e, h2e, sorb, nele, noA, noB, 1e30)
+    assert xk.shape == (0, comb.size(2)) and hk.numel() == 0 and not off.any()
+    e0 = ops.get_comb_hij_reduced(x[:0], h1e, h2e, sorb, nele, noA, noB, 1e-3)
+    assert e0[0].shape == (0, comb.size(2)) and e0[3].numel() == 1

@@ -49,3 +49,15 @@ def fe2s2():
     g = load("fe2s2_integrals")
     return dict(h1e=g["h1e"], h2e=g["h2e"], ci=g["ci_space"], sorb=int(g["sorb"]), noA=int(g["noA"]), noB=int(g["noB"]),
                 nele=int(g["nele"]))
+
+
+def toy_amplitude(states, sorb: int, cplx: bool):
+    """The stand-in ansatz of the REDUCE goldens (same as tests/golden/make_golden.py:toy_amplitude): psi(x) from
+    the +-1 occupation tensor [K, sorb] (torch, any device)."""
+    import torch
+
+    g = torch.Generator().manual_seed(77)
+    w = torch.randn(sorb, 2, generator=g, dtype=torch.float64).to(states.device)
+    z = states.to(torch.float64) @ w
+    amp = 0.3 + torch.tanh(0.11 * z[:, 0]) ** 2
+    return amp * torch.exp(1j * 0.7 * z[:, 1]) if cplx else amp * torch.sign(torch.cos(0.9 * z[:, 1]))
