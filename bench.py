@@ -405,6 +405,17 @@ def time_api_path(ops, dev, d_keys, d_psi, h1e, h2e, M, peak, prof, chunk=32768,
     flat = comb.view(-1, 8)
     l_ms, _ = t(lambda: ops.wavefunction_lut(lut.bra_key, flat, SORB, hash_index=lut.hash_index))
     fb, lb = (16 * M + 8) * chunk, 17 * M * chunk
+    # REDUCE method: kept rows only; eps at the 90th percentile of |H| of the first samples
+    eps = float(torch.quantile(hmat[:64].abs().flatten()[:: 7], 0.9))
+    del comb, hmat, flat
+    r_ms, (xk, hk, ik, off) = t(lambda: ops.get_comb_hij_reduced(x, h1e, h2e, SORB, NELE, NOA, NOB, eps, prepared=prep))
+    kept = int(ik.numel())
+    rb = kept * (8 + 8 + 8) + 8 * (chunk + 1)
+    reduce_entry = {"bound": "issue", "kernel": "reduce_kernel<1,double> count + emit (+ diag, scan) = get_comb_hij_reduced, eps = %.3g" % eps,
+                    "ms": r_ms, "samples_per_s": chunk / r_ms * 1e3, "rows_per_s": chunk * M / r_ms * 1e3, "kept_fraction": kept / (chunk * M),
+                    "output_bytes_per_launch": rb, "samples_per_launch": chunk,
+                    "note": "two passes over the rows (count, emit) instead of writing and re-reading [n, M] arrays; includes the "
+                            "host read of K between them"}
     return [
         {"bound": "hbm", "kernel": "enumerate_kernel<1,double,true> (+diag_kernel) = get_comb_hij_fused", "achieved": fb / f_ms / 1e6,
          "peak": peak, "unit": "GB/s", "frac": fb / f_ms / 1e6 / peak, "traffic": prof.get("enumerate_dram_bytes_per_launch"),
@@ -412,6 +423,7 @@ def time_api_path(ops, dev, d_keys, d_psi, h1e, h2e, M, peak, prof, chunk=32768,
         {"bound": "hbm", "kernel": "lut_indexed_kernel<1> = wavefunction_lut", "achieved": lb / l_ms / 1e6, "peak": peak,
          "unit": "GB/s", "frac": lb / l_ms / 1e6 / peak, "traffic": prof.get("lut_dram_bytes_per_launch"),
          "algorithmic_bytes_per_launch": lb, "samples_per_launch": chunk, "ms": l_ms, "samples_per_s": chunk / l_ms * 1e3},
+        reduce_entry,
     ]
 
 
