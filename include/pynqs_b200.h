@@ -154,6 +154,10 @@ int64_t pynqs_sort_bytes(int64_t N);
 int pynqs_sort_table(const uint8_t *key, const void *psi, int64_t N, int L, int sorb, int psi_bytes, uint8_t *key_out,
                      void *psi_out, int64_t *perm_out, void *ws, int64_t ws_bytes, void *stream);
 
+/* merge_rank_sample (libs/C_extension.pyi:256-279; cpu_tensor.cpp:537-556): out int64[length] = 0, then
+ * out[idx[i]] += counts[i] for i < n (int64 atomics; indices outside [0, length) are ignored). */
+int pynqs_merge_rank_sample(const int64_t *idx, const int64_t *counts, int64_t n, int64_t length, int64_t *out, void *stream);
+
 /* ---- energy statistics (utils/stats/dist_stats.py:18-79) -----------------------------------------
  * out[7] = { sum w, sum w Re d, sum w Im d, sum w |d|^2, Re c, Im c, n } with d = eloc - c, c = eloc[0];
  * eloc: double[n] or interleaved complex128[n] (eloc_complex).  weight_kind 0: w = weight (double[n]);

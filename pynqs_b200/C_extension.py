@@ -578,10 +578,19 @@ def weighted_moments(eloc: Tensor, weight: Tensor, weight_is_amplitude: bool = F
 
 # ---- names outside the hot path that callers import -----------------------
 def merge_rank_sample(idx: Tensor, counts: Tensor, split_idx: Tensor, length: int) -> Tensor:
-    """merge_counts[idx[i]] += counts[i] (C_extension.pyi:256-279); torch index_add_ (atomic, unlike
-    the reference's non-atomic kernel, cuda/kernel.cu:520-536)."""
-    out = torch.zeros(length, dtype=counts.dtype, device=counts.device)
-    return out.index_add_(0, idx, counts)
+    """merge_counts[idx[i]] += counts[i] (C_extension.pyi:256-279; merge_sample_cpu, cpu_tensor.cpp:537-556):
+    int64 [length].  Integer atomics, so `split_idx` (which the reference's non-atomic CUDA kernel needs to keep
+    equal indices apart, cuda/kernel.cu:520-536) is accepted and ignored."""
+    dev = _need_cuda(idx, counts)
+    idx = idx.to(torch.int64).contiguous()
+    counts = counts.to(torch.int64).contiguous()
+    if idx.dim() != 1 or counts.shape != idx.shape:
+        raise ValueError("idx and counts must be 1-D of equal length")
+    out = torch.empty(int(length), dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().pynqs_merge_rank_sample(vp(idx.data_ptr()), vp(counts.data_ptr()), i64(idx.numel()), i64(length),
+                                                       vp(out.data_ptr()), _stream(dev)))
+    return out
 
 
 def compress_h1e_h2e(h1e: np.ndarray, h2e: np.ndarray, sorb: int):

@@ -16,7 +16,7 @@ SYMBOLS = [
     "pynqs_lut", "pynqs_hash_bytes", "pynqs_hash_build", "pynqs_lut_hashed",
     "pynqs_group_bytes", "pynqs_group_build", "pynqs_eloc_scratch_bytes", "pynqs_eloc_sample_space",
     "pynqs_reduce_scratch_bytes", "pynqs_reduce_count", "pynqs_reduce_emit", "pynqs_reduce_eloc",
-    "pynqs_sort_bytes", "pynqs_sort_table", "pynqs_moments_scratch_bytes", "pynqs_weighted_moments",
+    "pynqs_merge_rank_sample", "pynqs_sort_bytes", "pynqs_sort_table", "pynqs_moments_scratch_bytes", "pynqs_weighted_moments",
     "pynqs_launch_count",
 ]
 

@@ -61,6 +61,7 @@ int launch_reduce(const u64 *, const T *, const T *, const void *, long long, co
                   long long *, u64 *, T *, long long *, cudaStream_t);
 int launch_reduce_eloc(const double *, int, const double *, const long long *, const long long *, long long, long long, double *,
                        double *, cudaStream_t);
+int launch_merge_counts(const long long *, const long long *, long long, long long, long long *, cudaStream_t);
 int launch_onv_to_tensor(const u64 *, void *, int, long long, int, cudaStream_t);
 int launch_tensor_to_onv(const unsigned char *, unsigned char *, long long, int, cudaStream_t);
 
@@ -349,6 +350,15 @@ int pynqs_sort_table(const uint8_t *key, const void *psi, int64_t N, int L, int 
   }
   return launch_sort_table(reinterpret_cast<const u64 *>(key), psi, N, L, sorb, psi_bytes, reinterpret_cast<u64 *>(key_out), psi_out,
                            reinterpret_cast<long long *>(perm_out), ws, ws_bytes, (cudaStream_t)stream);
+}
+
+int pynqs_merge_rank_sample(const int64_t *idx, const int64_t *counts, int64_t n, int64_t length, int64_t *out, void *stream) {
+  if (n < 0 || length < 0) {
+    set_error("merge_rank_sample: bad n = %lld or length = %lld", (long long)n, (long long)length);
+    return PYNQS_EVALUE;
+  }
+  return launch_merge_counts(reinterpret_cast<const long long *>(idx), reinterpret_cast<const long long *>(counts), n, length,
+                             reinterpret_cast<long long *>(out), (cudaStream_t)stream);
 }
 
 int64_t pynqs_moments_scratch_bytes(void) { return moments_scratch_bytes(); }

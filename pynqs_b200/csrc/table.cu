@@ -112,6 +112,29 @@ int launch_sort_table(const u64 *key, const void *psi, long long N, int L, int s
   return check_launch("table sort");
 }
 
+// ---- merge of per-rank sample counts --------------------------------------------------------------------
+// merge_counts[idx[i]] += counts[i]  (merge_sample_cpu, cpp_src/tensor/cpu_tensor.cpp:537-556).  64-bit integer
+// atomics: exact and order-independent (the reference's CUDA kernel adds without atomics, cuda/kernel.cu:520-536,
+// and relies on split_idx to keep equal indices apart).  Indices outside [0, length) are ignored.
+__global__ void __launch_bounds__(256)
+merge_counts_kernel(const long long *__restrict__ idx, const long long *__restrict__ counts, long long n, long long length,
+                    unsigned long long *__restrict__ out) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long k = idx[i];
+    if (k >= 0 && k < length) atomicAdd(out + k, (unsigned long long)counts[i]);
+  }
+}
+
+int launch_merge_counts(const long long *idx, const long long *counts, long long n, long long length, long long *out, cudaStream_t st) {
+  if (length > 0 && cudaMemsetAsync(out, 0, 8 * (size_t)length, st) != cudaSuccess) return check_launch("merge memset");
+  if (n == 0 || length == 0) return 0;
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  merge_counts_kernel<<<(unsigned)blocks, 256, 0, st>>>(idx, counts, n, length, reinterpret_cast<unsigned long long *>(out));
+  count_launch();
+  return check_launch("merge_counts_kernel");
+}
+
 // ---- weighted moments ---------------------------------------------------------------------------
 // out[0..6] = { sum w, sum w d_re, sum w d_im, sum w |d|^2, c_re, c_im, n }, d = E - c, c = E[0]
 // (shifted moments: |d| is of the size of the spread, so the variance has no cancellation).

@@ -602,3 +602,17 @@ def test_reduced_rows_against_oracle_and_fused(name):
     assert xk.shape == (0, comb.size(2)) and hk.numel() == 0 and not off.any()
     e0 = ops.get_comb_hij_reduced(x[:0], h1e, h2e, sorb, nele, noA, noB, 1e-3)
     assert e0[0].shape == (0, comb.size(2)) and e0[3].numel() == 1
+
+
+def test_merge_rank_sample_matches_the_reference_loop():
+    """merge_counts[idx[i]] += counts[i] (cpu_tensor.cpp:537-556) incl. repeated indices, empty input, length 0."""
+    rng = np.random.default_rng(17)
+    idx = rng.integers(0, 5000, size=200_000)
+    cnt = rng.integers(1, 1000, size=200_000)
+    want = np.zeros(5000, dtype=np.int64)
+    np.add.at(want, idx, cnt)
+    got = ops.merge_rank_sample(dev(idx), dev(cnt), torch.empty(0, device=DEV), 5000)
+    assert got.dtype == torch.int64
+    np.testing.assert_array_equal(got.cpu().numpy(), want)
+    assert not ops.merge_rank_sample(dev(idx[:0]), dev(cnt[:0]), torch.empty(0, device=DEV), 7).any()
+    assert ops.merge_rank_sample(dev(idx[:0]), dev(cnt[:0]), torch.empty(0, device=DEV), 0).numel() == 0
