@@ -1,2 +1,2 @@
 mkdir -p gpurun_out
-(timeout 1200 python -m pytest tests/test_gpu_parity.py -m gpu -x -q 2>&1 | tail -25) > gpurun_out/pytest_gpu.log 2>&1; tail -25 gpurun_out/pytest_gpu.log
+(timeout 1500 python -m pytest tests/test_gpu_parity.py -m gpu -x -q --durations=5 2>&1 | tail -25) > gpurun_out/pytest_gpu.log 2>&1; tail -25 gpurun_out/pytest_gpu.log

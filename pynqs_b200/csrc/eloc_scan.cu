@@ -226,25 +226,33 @@ constexpr int kDupWords = 512;     // 16384-bit filter for "two of my groups sha
 
 struct ScanSmem {
   u32 ypat, msk, rng, dup, lgrp, clist, queues, total;
+  u32 list_chunks;  // groups of up to list_chunks * 32 keys go to the flat chunk list (0: none -- everything by the warp)
 };
+constexpr u32 kScanSmemMax = 200 * 1024;
 __host__ __device__ inline ScanSmem scan_smem(const ExcGeom &g, int warps) {
   const size_t sB = (size_t)g.noB * g.nvB, nG = sB + 2;
   ScanSmem m;
-  size_t o = (sizeof(OrbLists) + 15) & ~(size_t)15;
-  m.ypat = (u32)o;
-  o += 8 * nG * g.L;
-  m.msk = (u32)o;
-  o += 8 * (size_t)table_offsets(g).total;
-  m.rng = (u32)o;
-  o += 8 * nG;
-  m.dup = (u32)o;
-  o += 4 * kDupWords;
-  m.lgrp = (u32)o;
-  o = (o + 2 * (sB + 2) + 15) & ~(size_t)15;
-  m.clist = (u32)o;
-  o += 16 * (sB * kListChunks + 8);
-  m.queues = (u32)o;
-  m.total = (u32)(o + sizeof(u32) * kQueue * warps);
+  // the chunk list is the one part that can be cut down when a large system would not fit: fewer chunks per
+  // group qualify, the rest of the groups is walked one warp per group
+  for (int lc = kListChunks;; lc = lc / 2) {
+    size_t o = (sizeof(OrbLists) + 15) & ~(size_t)15;
+    m.ypat = (u32)o;
+    o += 8 * nG * g.L;
+    m.msk = (u32)o;
+    o += 8 * (size_t)table_offsets(g).total;
+    m.rng = (u32)o;
+    o += 8 * nG;
+    m.dup = (u32)o;
+    o += 4 * kDupWords;
+    m.lgrp = (u32)o;
+    o = (o + 2 * (sB + 2) + 15) & ~(size_t)15;
+    m.clist = (u32)o;
+    o += 16 * (sB * lc + 8);
+    m.queues = (u32)o;
+    m.total = (u32)(o + sizeof(u32) * kQueue * warps);
+    m.list_chunks = (u32)lc;
+    if (m.total <= kScanSmemMax || lc == 0) break;
+  }
   return m;
 }
 
@@ -312,7 +320,7 @@ eloc_scan_kernel(const u64 *__restrict__ bra, long long n, GroupView gv, HitRun 
     if (q < g_begin || q >= g_end || r.y == r.x) return 0u;
     if (q >= sB) return 1u << 16;
     const u32 nc = (r.y - r.x + 31u) >> 5;
-    return nc > (u32)kListChunks ? (1u << 16) : nc;
+    return nc > sm.list_chunks ? (1u << 16) : nc;
   };
   auto warp_scan = [&](u32 v) -> u32 {
 #pragma unroll
@@ -726,6 +734,10 @@ static int launch_eloc_LC(const u64 *bra, long long n, const double *h1e, const 
   u32 *hits = reinterpret_cast<u32 *>(scratch + lay.hits);
   const ScanSmem sm = scan_smem(g, lay.warps);
   const size_t smem = sm.total;
+  if (smem > 227 * 1024) {
+    set_error("eloc: %zu bytes of shared memory per CTA needed for sorb = %d, noA = %d, noB = %d (limit 227 KB)", smem, g.sorb, g.noA, g.noB);
+    return 1;
+  }
   auto scan = lay.warps == 2 ? eloc_scan_kernel<L, HALF, 64> : (lay.warps == 4 ? eloc_scan_kernel<L, HALF, 128> : eloc_scan_kernel<L, HALF, 256>);
   if (smem > 48 * 1024 && cudaFuncSetAttribute(scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return check_launch("eloc_scan_kernel smem opt-in");

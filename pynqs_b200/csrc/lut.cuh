@@ -126,13 +126,6 @@ __device__ __forceinline__ bool tags_match(const uint4 &t, u32 tag) {
   return t.x == tag || t.y == tag || t.z == tag || (t.w | 1u) == tag;
 }
 __device__ __forceinline__ bool bucket_overflowed(const uint4 &t) { return t.w != 0u && !(t.w & 1u); }
-// branch-free "this probe cannot be rejected": 0 iff a tag matches or the bucket has overflowed.
-// (stored tags end in binary 11; an overflowed bucket's last tag ends in 10; empty slots are 0)
-__device__ __forceinline__ u32 probe_residue(const uint4 &t, u32 tag) {
-  const u32 a = min(t.x ^ tag, t.y ^ tag), b = min(t.z ^ tag, (t.w | 1u) ^ tag);
-  return min(min(a, b), (t.w & 3u) ^ 2u);
-}
-
 // region descriptor packed in 64 bits: off | lg << 32; kNoRegion when the group does not exist
 constexpr u64 kNoRegion = ~0ull;
 

@@ -12,8 +12,7 @@
 // are built once per CTA by all threads, and replace the reference's per-row
 // unpack_SinglesDoubles (15 div/mod + sqrt) by one exact multiply-shift division and two
 // shared-memory loads.  Each entry also carries what the row needs next: the offset of its
-// integral in the prepared tables and the sign bits (HitInfo below), and in the local-energy
-// kernel the hash / region descriptor of the excited string (eloc.cu).
+// integral in the prepared tables and the sign bits (HitInfo below).
 #pragma once
 #include "common.cuh"
 
@@ -121,35 +120,6 @@ __device__ __forceinline__ double flip_sign(double v, u32 bits) {
 }
 __device__ __forceinline__ float flip_sign(float v, u32 bits) {
   return __int_as_float(__float_as_int(v) ^ (int)(bits & 0x80000000u));
-}
-
-// which two entries make row r (r in [0, nsd)); returns the class: 0/1 single a/b, 2/3 aa/bb, 4 ab
-__device__ __forceinline__ int row_entries(const ExcGeom &g, const TableOffsets &to, int r, int &t1, int &t2) {
-  if (r >= g.d3) {
-    const u32 q = (u32)(r - g.d3);
-    const u32 jb = fdiv(q, g.by_sA);
-    t1 = to.sa + (int)(q - jb * g.sA);
-    t2 = to.sb + (int)jb;
-    return 4;
-  }
-  if (r >= g.d2) {
-    t1 = to.hpb + (int)((u32)r - fdiv((u32)r, g.by_noBB) * g.noBB);
-    t2 = to.ppb + (int)fdiv((u32)(r - g.d2), g.by_noBB);
-    return 3;
-  }
-  if (r >= g.d1) {
-    t1 = to.hpa + (int)((u32)r - fdiv((u32)r, g.by_noAA) * g.noAA);
-    t2 = to.ppa + (int)fdiv((u32)(r - g.d1), g.by_noAA);
-    return 2;
-  }
-  if (r >= g.d0) {
-    t1 = to.sb + (r - g.d0);
-    t2 = -1;
-    return 1;
-  }
-  t1 = to.sa + r;
-  t2 = -1;
-  return 0;
 }
 
 }  // namespace pynqs

@@ -459,6 +459,21 @@ def test_192_sorb_three_words_against_oracle():
         comb, hmat = ops.get_comb_hij_fused(dev(bra), dev(h1e_np), h2e, sorb, 8, noA, noB, prepared=prepared)
         np.testing.assert_array_equal(comb.cpu().numpy(), want_c)
         np.testing.assert_array_equal(hmat.cpu().numpy(), want_h)
+    # one-pass E_loc with 30a30b: 1982 groups per sample, M = 5.8 million -- the scan kernel's shared memory only
+    # fits with a shortened chunk list (one chunk per group), the rest of the groups are walked one warp each
+    noA = noB = 30
+    seed = S.random_onvs(1, sorb, noA, noB, seed=8)
+    comb = O.comb(seed, sorb, noA, noB).reshape(-1, 24)
+    rng = np.random.default_rng(9)
+    keys = np.unique(np.concatenate([seed, comb[rng.permutation(comb.shape[0])[:20000]]]), axis=0)
+    del comb
+    psi = S.random_psi(keys.shape[0], seed=10)
+    lut = WavefunctionLUT(dev(keys), dev(psi), sorb, DEV, rank=0, world_size=1)
+    x = np.concatenate([seed, keys[:3]])
+    e1, _, _ = local_energy_sample_space(dev(x), dev(h1e_np), h2e, lut, sorb, 60, noA, noB)
+    order = O.sort_onv(keys)
+    want = O.eloc_sample_space(x[:2], h1e_np, h2e_np, keys[order], psi[order], sorb, 60, noA, noB)
+    np.testing.assert_allclose(e1[:2].cpu().numpy(), want, rtol=1e-12, atol=0)
 
 
 # ---- the steps either side of the kernels: table sort, energy moments -------------------------------
