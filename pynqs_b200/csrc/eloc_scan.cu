@@ -622,18 +622,20 @@ eloc_eval_kernel(const u64 *__restrict__ bra, long long n, const double *__restr
           y = load_onv<L>((grouping ? gv.keys[1] : gv.keys[0]) + (size_t)pos * L);
           bool ok = true;
           if (HALF) {  // the scan tested one folded string only: class of the full key vs the scan it came from
+            // (bitwise logic, no short-circuit branches: the lanes must stay together)
             const u64 d = y.w[0] ^ x.w[0];
             const int na = __popcll(d & kEven), nb = __popcll(d & kOdd);
-            if (!(h & kHitOwn)) ok = na == 2 && nb == 2;               // alpha-beta double (bucket of a beta single)
-            else if (!grouping) ok = nb == 0 && (na == 2 || na == 4);  // own beta string
-            else ok = na == 0 && (nb == 2 || nb == 4);                 // own alpha string
+            const int moved = grouping ? nb : na, fixed = grouping ? na : nb;     // own-string scans: one string is x's
+            const bool ok_own = (fixed == 0) & ((moved == 2) | (moved == 4));     // single / same-spin double
+            const bool ok_ab = (na == 2) & (nb == 2);                             // alpha-beta double (bucket of a beta single)
+            ok = (h & kHitOwn) ? ok_own : ok_ab;
           }
           if (ok) {
             kind = excitation_class<L>(x, y);
             id = (long long)__ldg((grouping ? gv.rows[1] : gv.rows[0]) + pos);
           }
         }
-        if (kind == 2) accumulate<CPLX>(acc, load_psi<CPLX>(psi, id), p0, rederived_element<L, double>(x, y, h1e, h2e, g.sorb, g.nele));
+        if (kind == 2) accumulate<CPLX>(acc, load_psi<CPLX>(psi, id), p0, double_element<L, double>(x, y, h2e));
         // single excitations (rare): one at a time by the whole warp, terms gathered in parallel
         u32 pend = __ballot_sync(0xffffffffu, kind == 1);
         while (pend) {

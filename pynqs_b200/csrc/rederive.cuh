@@ -71,6 +71,46 @@ __device__ __forceinline__ int excitation_class(const Onv<L> &x, const Onv<L> &y
   return (nc == 1 && na == 1) ? 1 : ((nc == 2 && na == 2) ? 2 : 0);
 }
 
+// the two set bits of m (exactly two are set): highest and lowest position, without data-dependent branches
+template <int L>
+__device__ __forceinline__ void two_set_bits(const Onv<L> &m, u32 &hi, u32 &lo) {
+  hi = 0;
+  lo = 0;
+  bool have = false;
+#pragma unroll
+  for (int i = 0; i < L; ++i) {
+    const u64 w = m.w[i];
+    const bool nz = w != 0;
+    const u32 top = (u32)(64 * i + 63 - __clzll((long long)(w | 1ull)));
+    const u32 bot = (u32)(64 * i + __ffsll((long long)w) - 1);
+    hi = nz ? top : hi;  // later (more significant) words win
+    lo = (nz && !have) ? bot : lo;
+    have = have || nz;
+  }
+}
+
+// Double excitation x -> y (two bra-only and two ket-only orbitals) from the bit strings, branch-free so that the
+// lanes of a warp stay together: the same value as rederived_element / exc_element.
+template <int L, typename T>
+__device__ __forceinline__ T double_element(const Onv<L> &x, const Onv<L> &y, const T *__restrict__ h2e) {
+  Onv<L> cre, ann;
+#pragma unroll
+  for (int i = 0; i < L; ++i) {
+    const u64 d = x.w[i] ^ y.w[i];
+    cre.w[i] = d & x.w[i];
+    ann.w[i] = d & y.w[i];
+  }
+  u32 hh, hl, ph, pl;
+  two_set_bits<L>(cre, hh, hl);
+  two_set_bits<L>(ann, ph, pl);
+  const int par = count_below<L>(x, (int)hh) ^ count_below<L>(x, (int)hl) ^ count_below<L>(x, (int)ph) ^ count_below<L>(x, (int)pl);
+  const int cross = (int)(hh < ph) + (int)(hl < ph) + (int)(hh < pl) + (int)(hl < pl);
+  const int sg = par ^ cross ^ 1;
+  T v = (T)1.0 * __ldg(h2e + pair_offset(hh, hl, ph, pl));
+  v *= (sg & 1) ? (T)-1.0 : (T)1.0;
+  return v;
+}
+
 // Single excitation x -> y evaluated by a whole warp (all lanes pass the same x, y): the two-electron terms
 // of cpp_src/cpu/hamiltonian.cpp:52-72 are gathered one per lane and then added in the reference's order
 // (occ_order: words ascending, bits descending) through shuffles -- the same additions in the same order as
