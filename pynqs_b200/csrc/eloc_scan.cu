@@ -256,6 +256,9 @@ __host__ __device__ inline ScanSmem scan_smem(const ExcGeom &g, int warps) {
   return m;
 }
 
+// orbital (bit of the ONV word) of position f of a folded beta string (inverse of fold_beta)
+__device__ __forceinline__ u32 unfold_beta(u32 f) { return (f & 1u) ? 32u + f : f + 1u; }
+
 // hit word: position in the grouped copy | kHitA (alpha-grouped copy) | kHitOwn (found in the scan of one of
 // the sample's own strings, HALF route only -- the eval kernel checks the class of the key accordingly)
 constexpr u32 kHitA = 0x80000000u, kHitOwn = 0x40000000u, kHitPos = 0x3fffffffu;
@@ -282,6 +285,7 @@ eloc_scan_kernel(const u64 *__restrict__ bra, long long n, GroupView gv, HitRun 
   u32 *queues = reinterpret_cast<u32 *>(smem_raw + sm.queues);
   __shared__ int s_nchunks, s_nlong;
   __shared__ u32 s_flags, s_ndup;
+  __shared__ unsigned char s_bpos[32];
   __shared__ unsigned short s_dupq[kDupList];
   constexpr int kScanThreads = THREADS, kScanWarps = THREADS / 32;
   __shared__ u32 wtot[80];  // work per (round of THREADS groups, warp); nG <= 2306 -> at most 37 x 2 entries
@@ -300,9 +304,18 @@ eloc_scan_kernel(const u64 *__restrict__ bra, long long n, GroupView gv, HitRun 
     return;
   }
   const Onv<L> x = load_onv<L>(bra + s * L);
-  if (threadIdx.x < 64) build_lists<L>(x, g.sorb, g.noA, g.noB, lists, threadIdx.x, 64);
+  // HALF: the beta singles are picked straight out of the folded beta string (n-th set bit); the orbital lists
+  // are only built when a group has to be searched
+  if (!HALF && threadIdx.x < 64) build_lists<L>(x, g.sorb, g.noA, g.noB, lists, threadIdx.x, 64);
   if (HALF) {
     for (int t = threadIdx.x; t < kDupWords; t += kScanThreads) dupf[t] = 0u;
+    if (threadIdx.x < 32) {  // positions of the folded beta string: occupied ones first, then the virtual ones
+      const u32 occ = fold_beta(x.w[0]);
+      const u32 all = fold_beta(g.sorb >= 64 ? ~0ull : ((1ull << g.sorb) - 1ull));
+      const u32 bit = 1u << threadIdx.x, below = bit - 1u;
+      if (occ & bit) s_bpos[__popc(occ & below)] = (unsigned char)threadIdx.x;
+      else if (all & bit) s_bpos[g.noB + __popc(all & ~occ & below)] = (unsigned char)threadIdx.x;
+    }
   }
   if (threadIdx.x == 0) s_flags = s_ndup = 0u;
   __syncthreads();
@@ -330,15 +343,25 @@ eloc_scan_kernel(const u64 *__restrict__ bra, long long n, GroupView gv, HitRun 
     }
     return v;
   };
+  // one round of groups (and not an empty slice): every thread keeps the work scan of its only group
+  const bool one_round = q_hi > q_lo && q_hi - q_lo <= kScanThreads;
+  u32 my_work = 0, my_incl = 0;
+  uint2 my_r = make_uint2(0u, 0u);
   for (int q0 = q_lo; q0 < q_hi; q0 += kScanThreads) {
     const int q = q0 + (int)threadIdx.x;
     uint2 r = make_uint2(0u, 0u);
     if (q < q_hi) {
       Onv<L> y = x;
-      if (q < sB) {  // beta single q: hole = q % noB, particle = q / noB of the merged beta list
+      if (q < sB) {  // beta single q: hole number q % noB, particle number q / noB
         const u32 pb = fdiv((u32)q, g.by_noB), hb = (u32)q - pb * g.noB;
-        flip_bit<L>(y, lists.b[hb] & 0xff);
-        flip_bit<L>(y, lists.b[g.noB + pb] & 0xff);
+        if (HALF) {
+          // any fixed numbering of the occupied / virtual beta orbitals will do here (every group is treated
+          // alike): the order of the set bits of the folded string
+          y.w[0] ^= (1ull << unfold_beta(s_bpos[hb])) ^ (1ull << unfold_beta(s_bpos[g.noB + pb]));
+        } else {
+          flip_bit<L>(y, lists.b[hb] & 0xff);
+          flip_bit<L>(y, lists.b[g.noB + pb] & 0xff);
+        }
       }
       const int grouping = q == sB + 1 ? 1 : 0;
       const u32 bkt = group_bucket<L>(y, grouping, gv.shift);
@@ -361,7 +384,10 @@ eloc_scan_kernel(const u64 *__restrict__ bra, long long n, GroupView gv, HitRun 
         }
       }
     }
-    const u32 tot = __shfl_sync(0xffffffffu, warp_scan(work_of(q, r)), 31);
+    my_work = work_of(q, r);
+    my_incl = warp_scan(my_work);
+    my_r = r;
+    const u32 tot = __shfl_sync(0xffffffffu, my_incl, 31);
     if (lane == 0) wtot[(q0 - q_lo) / kScanThreads * kScanWarps + warp] = tot;
   }
   __syncthreads();
@@ -402,6 +428,10 @@ eloc_scan_kernel(const u64 *__restrict__ bra, long long n, GroupView gv, HitRun 
     __syncthreads();
   }
   if (flags & 1u) {
+    if (HALF) {  // the search route works on the excitation tables, which need the orbital lists
+      if (threadIdx.x < 64) build_lists<L>(x, g.sorb, g.noA, g.noB, lists, threadIdx.x, 64);
+      __syncthreads();
+    }
     const TableOffsets to = table_offsets(g);
     for_each_table_entry(g, lists, to, [&](int t, int, u32 e0, u32 e1) { msk[t] = msk_make<L>(e0 & 0xffu, e1 & 0xffu); });
     if (threadIdx.x == 0) {
@@ -411,7 +441,33 @@ eloc_scan_kernel(const u64 *__restrict__ bra, long long n, GroupView gv, HitRun 
     }
   }
   // every thread places the work of its groups: chunk list in group order, then the long list
-  {
+  auto place = [&](int q, uint2 r, u32 mine, u32 at) {
+    if (mine >> 16) {
+      lgrp[at >> 16] = (unsigned short)q;
+    } else if (mine) {
+      uint4 ent = make_uint4(r.x, r.y, (u32)q, 0u);
+      if (L == 1 && !HALF) {
+        ent.z = (u32)ypat[q];
+        ent.w = (u32)(ypat[q] >> 32);
+      }
+      for (u32 j = 0; j < mine; ++j) {
+        if (HALF) clist2[(at & 0xffffu) + j] = make_uint2(ent.x, ent.y);
+        else clist4[(at & 0xffffu) + j] = ent;
+        ent.x += 32u;
+      }
+    }
+  };
+  u32 all_work = 0;
+  if (one_round && !(flags & 2u)) {  // the common case: the scan of the bucket phase is still valid
+    u32 before = 0;
+#pragma unroll
+    for (int w = 0; w < kScanWarps; ++w) {
+      const u32 t = wtot[w];
+      before += w < warp ? t : 0u;
+      all_work += t;
+    }
+    place(q_lo + (int)threadIdx.x, my_r, my_work, before + my_incl - my_work);
+  } else {
     u32 before = 0;  // work of all the (round, warp) pairs before mine
     int slot = 0;
     for (int q0 = q_lo; q0 < q_hi; q0 += kScanThreads) {
@@ -419,33 +475,22 @@ eloc_scan_kernel(const u64 *__restrict__ bra, long long n, GroupView gv, HitRun 
       const int q = q0 + (int)threadIdx.x;
       const uint2 r = q < q_hi ? rng[q] : make_uint2(0u, 0u);
       const u32 mine = work_of(q, r);
-      const u32 at = before + warp_scan(mine) - mine;
-      if (mine >> 16) {
-        lgrp[at >> 16] = (unsigned short)q;
-      } else if (mine) {
-        uint4 ent = make_uint4(r.x, r.y, (u32)q, 0u);
-        if (L == 1) {
-          ent.z = (u32)ypat[q];
-          ent.w = (u32)(ypat[q] >> 32);
-        }
-        for (u32 j = 0; j < mine; ++j) {
-          if (HALF) clist2[(at & 0xffffu) + j] = make_uint2(ent.x, ent.y);
-          else clist4[(at & 0xffffu) + j] = ent;
-          ent.x += 32u;
-        }
-      }
+      place(q, r, mine, before + warp_scan(mine) - mine);
       for (int w = warp; w < kScanWarps; ++w) before += wtot[slot + w];
       slot += kScanWarps;
     }
-    // `before` now is the total: pad the chunk list to a whole number of unrolled iterations with empty chunks
-    const u32 nch = before & 0xffffu, padded = (nch + (u32)UN - 1u) / (u32)UN * (u32)UN;
+    all_work = before;
+  }
+  {
+    // pad the chunk list to a whole number of unrolled iterations with empty chunks
+    const u32 nch = all_work & 0xffffu, padded = (nch + (u32)UN - 1u) / (u32)UN * (u32)UN;
     if (threadIdx.x < padded - nch) {
       if (HALF) clist2[nch + threadIdx.x] = make_uint2(0u, 0u);
       else clist4[nch + threadIdx.x] = make_uint4(0u, 0u, (u32)g_begin, 0u);
     }
     if (threadIdx.x == 0) {
       s_nchunks = (int)padded;
-      s_nlong = (int)(before >> 16);
+      s_nlong = (int)(all_work >> 16);
     }
   }
   __syncthreads();
