@@ -13,11 +13,13 @@
 //         g = sB : the bucket of x's own beta string: alpha singles (distance 2), alpha-alpha
 //                  doubles (4) and x itself (0);
 //         g = sB+1: the bucket of x's own alpha string: beta singles and beta-beta doubles.
-//       A warp takes a group at a time, lanes take consecutive keys: coalesced loads, ~10
-//       instructions per key, no hashing and no searching.  Buckets much larger than the number of
+//       Small groups are cut into 32-key chunks and the chunks of a sample form one flat list that
+//       the warps consume evenly (lanes take consecutive keys: coalesced loads, ~16 instructions per
+//       32 keys, no hashing and no searching); one-word ONVs are tested on 32-bit folded strings.
+//       Larger groups are walked by one warp each; buckets much larger than the number of
 //       determinants they could contain are searched instead (binary search inside the bucket, the
 //       reference's own algorithm on a short range).  Hits go to per-warp queues (ballot + popcount
-//       compaction) and from there to a global candidate buffer in a deterministic order.
+//       compaction) and from there to a global hit buffer in a deterministic order.
 //   eloc_eval_kernel   one warp per sample: for every hit, <x|H|x'> re-derived from the two bit
 //       strings (rederive.cuh: same arithmetic, same order of additions as the fused operator)
 //       times psi(x') / psi(x), summed over a fixed lane assignment and a shuffle tree.
