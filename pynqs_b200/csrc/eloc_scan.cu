@@ -143,12 +143,12 @@ __device__ __forceinline__ u32 key_distance(const Onv<L> &k, const Onv<L> &y, u6
   return bad ? 255u : pc;
 }
 
-// scan the keys [s, e) of one bucket: two keys per lane in flight
+// walk the keys [s, e) of one bucket, this warp's share of it (warp `part` of `parts`): two keys per lane in flight
 template <int L>
 __device__ __forceinline__ void scan_bucket(const u64 *__restrict__ keys, u32 s, u32 e, const Onv<L> &y, u64 same, u32 allow, u32 gbit,
-                                            u32 *queue, u32 &qn, u32 *self_pos) {
+                                            u32 *queue, u32 &qn, u32 *self_pos, u32 part, u32 parts) {
   const u32 lane = threadIdx.x & 31;
-  for (u32 k0 = s; k0 < e; k0 += 64) {
+  for (u32 k0 = s + 64u * part; k0 < e; k0 += 64u * parts) {
     const u32 p0 = k0 + lane, p1 = p0 + 32;
     u32 d0 = 255u, d1 = 255u;
     Onv<L> a, b;
@@ -169,16 +169,21 @@ __device__ __forceinline__ void scan_bucket(const u64 *__restrict__ keys, u32 s,
 //   kind 0: alpha-beta doubles on top of a beta single, base = x with that single applied (targets: sA alpha singles)
 //   kind 1: own beta string  (targets: x itself, sA alpha singles, noAA * nvAA alpha-alpha doubles)
 //   kind 2: own alpha string (targets: sB beta singles, noBB * nvBB beta-beta doubles)
-// walk the folded strings [s, e) of one bucket (HALF route): distance of each to `pat`, allowed distances in `allow`
-__device__ __forceinline__ u32 scan_half(const u32 *__restrict__ half, u32 s, u32 e, u32 pat, u32 allow, u32 flags, u32 *queue, u32 qn) {
+// walk the folded strings [s, e) of one bucket (HALF route), this warp's share of it (warp `part` of `parts`):
+// distance of each to `pat`, allowed distances in `allow`; four loads per lane in flight
+__device__ __forceinline__ u32 scan_half(const u32 *__restrict__ half, u32 s, u32 e, u32 pat, u32 allow, u32 flags, u32 *queue, u32 qn,
+                                         u32 part, u32 parts) {
   const u32 lane = threadIdx.x & 31;
-  for (u32 k0 = s; k0 < e; k0 += 64) {
-    const u32 p0 = k0 + lane, p1 = p0 + 32;
-    u32 d0 = 31u, d1 = 31u;
-    if (p0 < e) d0 = (u32)__popc(__ldg(half + p0) ^ pat);
-    if (p1 < e) d1 = (u32)__popc(__ldg(half + p1) ^ pat);
-    push_hits(queue, qn, ((allow >> min(d0, 31u)) & 1u) != 0u, p0 | flags);
-    push_hits(queue, qn, ((allow >> min(d1, 31u)) & 1u) != 0u, p1 | flags);
+  for (u32 k0 = s + 128u * part; k0 < e; k0 += 128u * parts) {
+    u32 d[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const u32 p = k0 + 32u * u + lane;
+      d[u] = 31u;
+      if (p < e) d[u] = (u32)__popc(__ldg(half + p) ^ pat);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) push_hits(queue, qn, ((allow >> d[u]) & 1u) != 0u, (k0 + 32u * u + lane) | flags);
   }
   return qn;
 }
@@ -189,11 +194,11 @@ struct SearchGeom {  // per kind: number of single targets, hole pairs, particle
 
 template <int L>
 __device__ __noinline__ u32 search_bucket(const u64 *__restrict__ keys, u32 s, u32 e, const Onv<L> base, const u64 *msk,
-                                          const SearchGeom *sg, u32 gbit, u32 *queue, u32 qn, u32 *self_pos) {
+                                          const SearchGeom *sg, u32 gbit, u32 *queue, u32 qn, u32 *self_pos, int part, int parts) {
   const int lane = threadIdx.x & 31;
   const int nS = sg->nS, nH = sg->nH, nD = nH * sg->nP, oS = sg->oS, oH = sg->oH, oP = sg->oP;
   const int total = nS + nD + sg->self;
-  for (int t0 = 0; t0 < total; t0 += 32) {
+  for (int t0 = 32 * part; t0 < total; t0 += 32 * parts) {  // this warp's share of the targets
     const int t = t0 + lane;
     u32 pos = 0xffffffffu;
     bool self = false;
@@ -229,6 +234,7 @@ constexpr int kDupWords = 512;     // 16384-bit filter for "two of my groups sha
 struct ScanSmem {
   u32 ypat, msk, rng, dup, lgrp, clist, queues, total;
   u32 list_chunks;  // groups of up to list_chunks * 32 keys go to the flat chunk list (0: none -- everything by the warp)
+  u32 search_factor;  // a bucket this many times larger than the number of determinants it could hold is searched
 };
 constexpr u32 kScanSmemMax = 200 * 1024;
 __host__ __device__ inline ScanSmem scan_smem(const ExcGeom &g, int warps) {
@@ -255,6 +261,7 @@ __host__ __device__ inline ScanSmem scan_smem(const ExcGeom &g, int warps) {
     m.list_chunks = (u32)lc;
     if (m.total <= kScanSmemMax || lc == 0) break;
   }
+  m.search_factor = 64u;
   return m;
 }
 
@@ -325,8 +332,11 @@ eloc_scan_kernel(const u64 *__restrict__ bra, long long n, GroupView gv, HitRun 
   // ---- the groups of this slice: pattern and bucket of each ---------------------------------------------------
   const int per = (nG + splits - 1) / splits;
   const int g_begin = split * per, g_end = min(nG, g_begin + per), ab_end = min(g_end, sB);
-  const u32 big_ab = 16u * (u32)g.sA;  // an alpha-beta group this large is searched, not walked
-  const u32 big_own_b = 16u * (u32)(g.sA + g.noAA * g.nvAA + 1), big_own_a = 16u * (u32)(sB + g.noBB * g.nvBB);
+  // a group this large is searched, not walked.  Walking is ~16 instructions per 32 keys with independent
+  // loads; a search is ~13 dependent loads per determinant the group could hold: the break-even is at a few
+  // thousand keys for the 75 alpha singles of an Fe2S2 alpha-beta group, hence the default factor of 64
+  const u32 big_ab = sm.search_factor * (u32)g.sA;
+  const u32 big_own_b = sm.search_factor * (u32)(g.sA + g.noAA * g.nvAA + 1), big_own_a = sm.search_factor * (u32)(sB + g.noBB * g.nvBB);
   // (HALF: the buckets of ALL groups, so that every slice agrees on which group walks a shared bucket)
   const int q_lo = HALF ? 0 : g_begin, q_hi = HALF ? nG : g_end;
   constexpr int UN = HALF ? kHalfUnroll : kChunkUnroll;
@@ -539,26 +549,32 @@ eloc_scan_kernel(const u64 *__restrict__ bra, long long n, GroupView gv, HitRun 
       for (int u = 0; u < UN; ++u) push_hits(queue, qn, key_distance<L>(k[u], y[u], kOdd) == 2u, pos[u]);
     }
   }
-  // ---- (2) the own groups and the long alpha-beta groups: one warp per group ---------------------------------------
+  // ---- (2) the own groups and the long alpha-beta groups ---------------------------------------------------------
+  // Small ones (the two own groups of a sparse table, typically) go to one warp each; large ones are shared by
+  // all warps: a sample may have a few groups of thousands of keys next to dozens of small ones, and one warp
+  // per group would leave the others idle.
   const int nlong = s_nlong;
-  for (int i = warp; i < nlong; i += kScanWarps) {
+  for (int i = 0; i < nlong; ++i) {
     const int q = lgrp[i];
     const uint2 r = rng[q];
     const u32 size = r.y - r.x;
     if (size == 0) continue;
+    const bool shared = size > 256u;
+    if (!shared && i % kScanWarps != warp) continue;
+    const int part = shared ? warp : 0, parts = shared ? kScanWarps : 1;
     Onv<L> y;
 #pragma unroll
     for (int w = 0; w < L; ++w) y.w[w] = ypat[q * L + w];
     if (q < sB) {  // alpha-beta doubles on top of beta single q
-      if (size > big_ab) qn = search_bucket<L>(gv.keys[0], r.x, r.y, y, msk, &s_sg[0], 0u, queue, qn, nullptr);
-      else if (HALF) qn = scan_half(gv.half[0], r.x, r.y, fold_alpha(x.w[0]), 1u << 2, 0u, queue, qn);
-      else scan_bucket<L>(gv.keys[0], r.x, r.y, y, kOdd, 1u << 2, 0u, queue, qn, nullptr);
+      if (size > big_ab) qn = search_bucket<L>(gv.keys[0], r.x, r.y, y, msk, &s_sg[0], 0u, queue, qn, nullptr, part, parts);
+      else if (HALF) qn = scan_half(gv.half[0], r.x, r.y, fold_alpha(x.w[0]), 1u << 2, 0u, queue, qn, part, parts);
+      else scan_bucket<L>(gv.keys[0], r.x, r.y, y, kOdd, 1u << 2, 0u, queue, qn, nullptr, part, parts);
     } else if (q == sB) {  // own beta string: x itself, alpha singles, alpha-alpha doubles
       if (size > big_own_b) {
-        qn = search_bucket<L>(gv.keys[0], r.x, r.y, x, msk, &s_sg[1], HALF ? kHitOwn : 0u, queue, qn, self_pos + s);
+        qn = search_bucket<L>(gv.keys[0], r.x, r.y, x, msk, &s_sg[1], HALF ? kHitOwn : 0u, queue, qn, self_pos + s, part, parts);
       } else if (HALF) {
         const u32 ax = fold_alpha(x.w[0]);
-        for (u32 k0 = r.x; k0 < r.y; k0 += 32) {
+        for (u32 k0 = r.x + 32u * part; k0 < r.y; k0 += 32u * parts) {
           const u32 pos = k0 + (u32)lane;
           u32 d = 31u;
           if (pos < r.y) d = (u32)__popc(__ldg(gv.half[0] + pos) ^ ax);
@@ -566,15 +582,15 @@ eloc_scan_kernel(const u64 *__restrict__ bra, long long n, GroupView gv, HitRun 
           push_hits(queue, qn, d == 2u || d == 4u, pos | kHitOwn);
         }
       } else {
-        scan_bucket<L>(gv.keys[0], r.x, r.y, x, kOdd, (1u << 2) | (1u << 4), 0u, queue, qn, self_pos + s);
+        scan_bucket<L>(gv.keys[0], r.x, r.y, x, kOdd, (1u << 2) | (1u << 4), 0u, queue, qn, self_pos + s, part, parts);
       }
     } else {  // own alpha string: beta singles, beta-beta doubles
       if (size > big_own_a) {
-        qn = search_bucket<L>(gv.keys[1], r.x, r.y, x, msk, &s_sg[2], kHitA | (HALF ? kHitOwn : 0u), queue, qn, nullptr);
+        qn = search_bucket<L>(gv.keys[1], r.x, r.y, x, msk, &s_sg[2], kHitA | (HALF ? kHitOwn : 0u), queue, qn, nullptr, part, parts);
       } else if (HALF) {
-        qn = scan_half(gv.half[1], r.x, r.y, fold_beta(x.w[0]), (1u << 2) | (1u << 4), kHitA | kHitOwn, queue, qn);
+        qn = scan_half(gv.half[1], r.x, r.y, fold_beta(x.w[0]), (1u << 2) | (1u << 4), kHitA | kHitOwn, queue, qn, part, parts);
       } else {
-        scan_bucket<L>(gv.keys[1], r.x, r.y, x, kEven, (1u << 2) | (1u << 4), kHitA, queue, qn, nullptr);
+        scan_bucket<L>(gv.keys[1], r.x, r.y, x, kEven, (1u << 2) | (1u << 4), kHitA, queue, qn, nullptr, part, parts);
       }
     }
   }
@@ -781,7 +797,11 @@ static int launch_eloc_LC(const u64 *bra, long long n, const double *h1e, const 
   HitRun *runs = reinterpret_cast<HitRun *>(scratch + lay.runs);
   u32 *cursor = reinterpret_cast<u32 *>(scratch + lay.cursor);
   u32 *hits = reinterpret_cast<u32 *>(scratch + lay.hits);
-  const ScanSmem sm = scan_smem(g, lay.warps);
+  ScanSmem sm = scan_smem(g, lay.warps);
+  if (const char *e = getenv("PYNQS_SEARCH_FACTOR")) {  // parity tests: force the search route on small tables
+    const int f = atoi(e);
+    if (f >= 1 && f <= 4096) sm.search_factor = (u32)f;
+  }
   const size_t smem = sm.total;
   if (smem > 227 * 1024) {
     set_error("eloc: %zu bytes of shared memory per CTA needed for sorb = %d, noA = %d, noB = %d (limit 227 KB)", smem, g.sorb, g.noA, g.noB);

@@ -253,10 +253,13 @@ def test_eloc_sample_missing_from_table_gives_nan_like_reference():
     assert (psi_x[10:] == 0).all()
 
 
-def test_eloc_dense_table_full_space(scan_route):
+@pytest.mark.parametrize("search_factor", ["64", "8"])
+def test_eloc_dense_table_full_space(scan_route, search_factor, monkeypatch):
     """Full 24-spin-orbital space (6a6b, 853 776 keys): EVERY connected determinant is in the table
     (1819 hits per sample) and the groups are large enough (924 keys) for the alpha-beta groups to be
-    searched instead of scanned -- the result must equal the oracle and the three-call path."""
+    searched instead of walked when the threshold is lowered (factor 8) -- the result must equal the oracle and
+    the three-call path either way."""
+    monkeypatch.setenv("PYNQS_SEARCH_FACTOR", search_factor)
     sorb, noA, noB, nele = 24, 6, 6, 12
     import itertools
 
@@ -309,11 +312,13 @@ def test_eloc_hit_queue_overflow_takes_the_full_route(scan_route):
 
 
 @pytest.mark.parametrize("alpha_only", [True, False])
-def test_eloc_one_huge_group_is_searched(alpha_only, scan_route):
+def test_eloc_one_huge_group_is_searched(alpha_only, scan_route, monkeypatch):
     """36 spin orbitals, 9 electrons of ONE spin: the whole table (all 48 620 strings) is a single group,
-    35x larger than the 1378 determinants connected to a sample -> the own-string bucket is searched
-    (binary search inside the bucket) instead of scanned."""
+    35x larger than the 1378 determinants connected to a sample -> with the search threshold lowered to 16x the
+    own-string bucket is searched (binary search inside the bucket) instead of walked."""
     import itertools
+
+    monkeypatch.setenv("PYNQS_SEARCH_FACTOR", "16")
 
     sorb = 36
     noA, noB = (9, 0) if alpha_only else (0, 9)
