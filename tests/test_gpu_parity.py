@@ -360,6 +360,29 @@ def test_eloc_tiny_tables_many_groups_per_bucket(nkeys, scan_route):
     np.testing.assert_allclose(e1.cpu().numpy(), want, rtol=1e-12, atol=0)
 
 
+@pytest.mark.parametrize("sorb,noA,noB", [(40, 15, 15), (100, 3, 3)])
+def test_eloc_table_with_duplicate_keys_takes_the_reference_route(sorb, noA, noB):
+    """A table that holds some keys twice (the reference tolerates it: its binary search lands on one of the
+    copies): the build notices, and every sample is evaluated by full enumeration + the reference's probe
+    sequence, so even the choice among copies with DIFFERENT psi values is the reference's."""
+    seeds = S.random_onvs(3, sorb, noA, noB, seed=61)
+    comb = O.comb(seeds, sorb, noA, noB).reshape(-1, seeds.shape[1])
+    rng = np.random.default_rng(62)
+    keys = np.unique(np.concatenate([seeds, comb[rng.permutation(comb.shape[0])[:1500]]]), axis=0)
+    keys = np.concatenate([keys, keys[::7], keys[::31]])          # duplicates, some three times
+    psi = S.random_psi(keys.shape[0], seed=63)                     # different values on the copies
+    h1e, h2e = S.random_packed_integrals(sorb, seed=7, symmetric=True)
+    lut = WavefunctionLUT(dev(keys), dev(psi), sorb, DEV, rank=0, world_size=1)
+    x = np.concatenate([seeds, keys[:9]])
+    e1, _, p1 = local_energy_sample_space(dev(x), dev(h1e), dev(h2e), lut, sorb, noA + noB, noA, noB)
+    order = O.sort_onv(keys)
+    want = O.eloc_sample_space(x, h1e, h2e, keys[order], psi[order], sorb, noA + noB, noA, noB)
+    np.testing.assert_allclose(e1.cpu().numpy(), want, rtol=1e-12, atol=0)
+    e3, _, p3 = local_energy_three_call(dev(x), dev(h1e), dev(h2e), lut, sorb, noA + noB, noA, noB, batch=4)
+    np.testing.assert_allclose(e1.cpu().numpy(), e3.cpu().numpy(), rtol=1e-12, atol=0)
+    assert torch.equal(p1, p3)
+
+
 def test_eloc_multiword_onvs_against_oracle():
     """L = 2 (100 spin orbitals) and L = 3 (132): one-pass E_loc vs the oracle on a small table."""
     for sorb, noA, noB, nkeys in ((100, 3, 3, 4000), (132, 3, 2, 3000)):
