@@ -332,6 +332,8 @@ def run_ours(args):
             "traffic_note": "DRAM bytes per call from ncu (profiles/r01/traffic.json: %s B/sample): the table copies stay in L2" % per_sample_dram,
             "peak_source": peak_src, "algorithmic_bytes_per_sample": B, "algorithmic_bytes_per_launch": B * k_n,
             "samples_per_launch": k_n, "kernel_ms": k_ms,
+            "real_bound": {"what": "issue slots of eloc_scan_kernel (ncu, profiles/r01/eloc_kernels_ncu.txt, 136 400 samples per launch)",
+                           **prof.get("scan_kernel_ncu", {})},
             "note": "equivalent-bytes roofline per SURVEY.md 8(d): the one-pass kernels never write comb/Hmat/idx, so "
                     "'achieved' = API-path bytes (fused + lut, 259.9 KB/sample) / time and exceeds the HBM peak; they scan the "
                     "string-grouped table copies out of L2 and their real bound is the issue slots (profiles/). The kernels "
@@ -368,12 +370,30 @@ def run_ours(args):
 
 
 def load_profile_numbers():
-    """ncu-derived per-launch DRAM traffic of the committed profile (profiles/r01/traffic.json), if present."""
-    path = os.path.join(ROOT, "profiles", "r01", "traffic.json")
+    """ncu-derived numbers of the committed profile (profiles/r01/): per-launch DRAM traffic and, for the scan
+    kernel, the utilisation figures that say what really bounds it."""
+    out = {}
     try:
-        return json.load(open(path))
+        out = json.load(open(os.path.join(ROOT, "profiles", "r01", "traffic.json")))
     except Exception:
-        return {}
+        pass
+    try:
+        want = {"smsp__issue_active.avg.pct_of_peak_sustained_active": "issue_slots_busy_pct",
+                "lts__throughput.avg.pct_of_peak_sustained_elapsed": "l2_throughput_pct",
+                "dram__throughput.avg.pct_of_peak_sustained_elapsed": "dram_throughput_pct",
+                "sm__warps_active.avg.pct_of_peak_sustained_active": "occupancy_pct",
+                "gpu__time_duration.sum": "launch_us"}
+        scan = {}
+        for line in open(os.path.join(ROOT, "profiles", "r01", "eloc_kernels_ncu.txt")):
+            f = line.split()
+            if line.startswith("Kernel Name") and scan:
+                break  # first kernel of the report = eloc_scan_kernel
+            if f and f[0] in want:
+                scan[want[f[0]]] = float(f[1])
+        out["scan_kernel_ncu"] = scan
+    except Exception:
+        pass
+    return out
 
 
 def time_api_path(ops, dev, d_keys, d_psi, h1e, h2e, M, peak, prof, chunk=32768, reps=7):
