@@ -615,7 +615,7 @@ eloc_scan_kernel(const u64 *__restrict__ bra, long long n, GroupView gv, HitRun 
 
 // ---- evaluation ---------------------------------------------------------------------------------------------
 template <int L, bool CPLX, bool HALF>
-__global__ void __launch_bounds__(kEvalThreads)
+__global__ void __launch_bounds__(kEvalThreads, 12)
 eloc_eval_kernel(const u64 *__restrict__ bra, long long n, const double *__restrict__ h1e, const double *__restrict__ h2e,
                  const u64 *__restrict__ key, const double *__restrict__ psi, long long N, GroupView gv,
                  const HitRun *__restrict__ runs, const u32 *__restrict__ hits, const u32 *__restrict__ self_pos,
