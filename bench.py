@@ -326,13 +326,13 @@ def run_ours(args):
     prof = load_profile_numbers()
     per_sample_dram = prof.get("eloc_dram_bytes_per_sample")
     roof = {"bound": "hbm", "kernel": "eloc_scan_kernel<1,folded,128> (+ eloc_eval_kernel, diag_kernel): one-pass sample-space E_loc",
-            "launch": "one pynqs_eloc_sample_space call on this rank's samples = 1 diag kernel + one scan and one eval kernel per batch of <= 136 400 samples",
+            "launch": "one pynqs_eloc_sample_space call on this rank's samples = 1 diag kernel + one scan and one eval kernel per batch of <= 262 144 samples",
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "traffic": per_sample_dram * k_n if per_sample_dram else None,
             "traffic_note": "DRAM bytes per call from ncu (profiles/r01/traffic.json: %s B/sample): the table copies stay in L2" % per_sample_dram,
             "peak_source": peak_src, "algorithmic_bytes_per_sample": B, "algorithmic_bytes_per_launch": B * k_n,
             "samples_per_launch": k_n, "kernel_ms": k_ms,
-            "real_bound": {"what": "issue slots of eloc_scan_kernel (ncu, profiles/r01/eloc_kernels_ncu.txt, 136 400 samples per launch)",
+            "real_bound": {"what": "issue slots of eloc_scan_kernel (ncu, profiles/r01/eloc_kernels_ncu.txt, 262 144 samples per launch)",
                            **prof.get("scan_kernel_ncu", {})},
             "note": "equivalent-bytes roofline per SURVEY.md 8(d): the one-pass kernels never write comb/Hmat/idx, so "
                     "'achieved' = API-path bytes (fused + lut, 259.9 KB/sample) / time and exceeds the HBM peak; they scan the "

@@ -764,10 +764,10 @@ struct ElocScratch {
 static ElocScratch eloc_scratch_layout(long long n, const ExcGeom &g) {
   ElocScratch l;
   // hits per sample the global buffer can take before samples fall back to the full route, and a
-  // batch size that keeps the buffer at about 1 GiB
+  // batch size that keeps the buffer at about 2 GiB
   long long per_sample = (long long)g.nsd / 4;
   per_sample = per_sample < 256 ? 256 : (per_sample > 4096 ? 4096 : per_sample);
-  l.batch = (1LL << 28) / per_sample;
+  l.batch = (1LL << 29) / per_sample;
   l.batch = l.batch < 1024 ? 1024 : (l.batch > (1LL << 18) ? (1LL << 18) : l.batch);
   const long long nb = n < l.batch ? n : l.batch;
   l.warps = scan_threads(g.noB * g.nvB + 2) / 32;
