@@ -5,6 +5,8 @@
 //   2. sort   : one stable radix sort per grouping of (bucket id, row) over log2(buckets) bits
 //               (cub onesweep) -- rows inside a bucket stay ascending;
 //   3. finish : gather the keys into bucket order and write the bucket boundaries.
+#include <mutex>
+
 #include <cub/device/device_radix_sort.cuh>
 
 #include "gindex.cuh"
@@ -46,7 +48,7 @@ GroupLayout group_layout(long long N, int L) {
                                   (int)(N > 0 ? N : 1), 0, 32);
   l.cub_off = o;
   l.cub_bytes = tmp;
-  l.total = up(o + (long long)tmp) + 256;
+  l.total = up(o + 2 * (long long)up((long long)tmp)) + 256;  // one temporary area per (concurrent) sort
   return l;
 }
 
@@ -127,6 +129,31 @@ __global__ void __launch_bounds__(256) group_empty_kernel(GroupHeader *hdr, u32 
     startB[t] = startA[t] = 0u;
 }
 
+// The two sorts are independent and far too small to fill the GPU (10^6 keys: ~16 us per pass): the second one
+// runs on a side stream, forked from and joined back into the caller's stream with events (capturable).
+struct SideLane {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+};
+static std::mutex g_side_mutex;
+static SideLane g_side[64];
+
+static SideLane *side_lane() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  SideLane &s = g_side[dev];
+  if (s.stream == nullptr) {
+    if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) != cudaSuccess) {
+      s.stream = nullptr;
+      cudaGetLastError();
+      return nullptr;
+    }
+  }
+  return &s;
+}
+
 int launch_group_build(const u64 *key, long long N, int L, void *ws, long long ws_bytes, cudaStream_t st) {
   if (N >= (1LL << 31)) {
     set_error("the grouped table supports fewer than 2^31 keys (got %lld)", N);
@@ -164,16 +191,25 @@ int launch_group_build(const u64 *key, long long N, int L, void *ws, long long w
     default: set_error("unsupported ONV length L=%d", L); return 1;
   }
   count_launch();
+  std::lock_guard<std::mutex> lock(g_side_mutex);
+  SideLane *side = side_lane();
+  const bool forked = side != nullptr && cudaEventRecord(side->fork, st) == cudaSuccess &&
+                      cudaStreamWaitEvent(side->stream, side->fork, 0) == cudaSuccess;
+  if (!forked) cudaGetLastError();
+  const long long cub_stride = (l.cub_bytes + 255) / 256 * 256;
   for (int g = 0; g < 2; ++g) {
     size_t tmp = l.cub_bytes;
-    const cudaError_t e = cub::DeviceRadixSort::SortPairs(b + l.cub_off, tmp, (const u32 *)bkt[g][0], bkt[g][1], (const u32 *)iota,
-                                                          rows[g], (int)N, 0, (int)l.log2_buckets, st);
+    const cudaStream_t sg = (g == 1 && forked) ? side->stream : st;
+    const cudaError_t e = cub::DeviceRadixSort::SortPairs(b + l.cub_off + g * cub_stride, tmp, (const u32 *)bkt[g][0], bkt[g][1],
+                                                          (const u32 *)iota, rows[g], (int)N, 0, (int)l.log2_buckets, sg);
     if (e != cudaSuccess) {
       set_error("group sort: CUDA error %d (%s)", (int)e, cudaGetErrorString(e));
       return 3;
     }
     count_launch(((int)l.log2_buckets + 7) / 8 + 2);
   }
+  if (forked && (cudaEventRecord(side->join, side->stream) != cudaSuccess || cudaStreamWaitEvent(st, side->join, 0) != cudaSuccess))
+    return check_launch("group build join");
   const dim3 grid(blocks, 2);
 #define PYNQS_FINISH(LL)                                                                                                           \
   group_finish_kernel<LL><<<grid, 256, 0, st>>>(key, N, l.log2_buckets, bkt[0][1], bkt[1][1], rows[0], rows[1], keys[0], keys[1], \
