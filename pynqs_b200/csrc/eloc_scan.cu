@@ -229,7 +229,7 @@ constexpr int kListChunks = 4;     // groups of up to kListChunks * 32 keys go t
 constexpr int kChunkUnroll = 4;    // independent key loads in flight per lane (full keys)
 constexpr int kHalfUnroll = 8;     // ... (folded 32-bit strings)
 constexpr int kDupList = 32;       // suspects checked exactly (more: every group is checked)
-constexpr int kDupWords = 512;     // 16384-bit filter for "two of my groups share a bucket"
+constexpr int kDupLog2 = 9, kDupWords = 1 << kDupLog2;  // set of the bucket ids of a sample's groups (<= 256 of them)
 
 struct ScanSmem {
   u32 ypat, msk, rng, dup, lgrp, clist, queues, total;
@@ -296,6 +296,7 @@ eloc_scan_kernel(const u64 *__restrict__ bra, long long n, GroupView gv, HitRun 
   __shared__ u32 s_flags, s_ndup;
   __shared__ unsigned char s_bpos[32];
   __shared__ unsigned short s_dupq[kDupList];
+  __shared__ u32 s_kill[8];
   constexpr int kScanThreads = THREADS, kScanWarps = THREADS / 32;
   __shared__ u32 wtot[80];  // work per (round of THREADS groups, warp); nG <= 2306 -> at most 37 x 2 entries
   __shared__ SearchGeom s_sg[3];
@@ -386,13 +387,21 @@ eloc_scan_kernel(const u64 *__restrict__ bra, long long n, GroupView gv, HitRun 
       if (size > (q < sB ? big_ab : (q == sB ? big_own_b : big_own_a))) atomicOr(&s_flags, 1u);  // searched: needs the tables
       if (HALF && q < sB && size && size <= big_ab) {
         // the folded test cannot tell two beta strings in one bucket apart: a bucket must be WALKED for only one
-        // of the groups that map to it (searches are exact per group and stay).  Suspects (second arrival at a
-        // bit of the filter) are listed and checked exactly below.
-        const u32 bit = 1u << (bkt & 31u);
-        if (atomicOr(&dupf[(bkt >> 5) & (kDupWords - 1)], bit) & bit) {
-          const u32 at = atomicAdd(&s_ndup, 1u);
-          if (at < (u32)kDupList) s_dupq[at] = (unsigned short)q;
-          atomicOr(&s_flags, 2u);
+        // of the groups that map to it (searches are exact per group and stay).  Suspects (a later arrival at a
+        // bucket that is already in the set) are listed and resolved below.
+        // (a small open-addressing set of the bucket ids seen so far: exact, so the check below only runs for
+        //  samples that really have two groups in one bucket -- a fraction of a per cent)
+        u32 slot = (bkt * 0x9E3779B1u) >> (32 - kDupLog2);
+        for (;;) {
+          const u32 old = atomicCAS(&dupf[slot], 0u, bkt + 1u);
+          if (old == 0u) break;  // first group of this bucket
+          if (old == bkt + 1u) {
+            const u32 at = atomicAdd(&s_ndup, 1u);
+            if (at < (u32)kDupList) s_dupq[at] = (unsigned short)q;
+            atomicOr(&s_flags, 2u);
+            break;
+          }
+          slot = (slot + 1u) & (u32)(kDupWords - 1);
         }
       }
     }
@@ -405,17 +414,23 @@ eloc_scan_kernel(const u64 *__restrict__ bra, long long n, GroupView gv, HitRun 
   __syncthreads();
   const u32 flags = s_flags;
   if (flags & 2u) {  // rare: filter collision or two groups in one bucket -- keep the lowest group only
+    // decisions first (reads of the unchanged buckets, marks in a bit set), then the clearing: no thread reads a
+    // bucket that another one is clearing
+    if (threadIdx.x < 8) s_kill[threadIdx.x] = 0u;  // one-word ONVs: at most 256 alpha-beta groups
+    __syncthreads();
     const u32 nd = s_ndup;
     if (nd <= (u32)kDupList) {
-      // one of the groups of a shared bucket arrived first and is not listed, so a suspect clears the HIGHER of
-      // every equal pair it finds; the lowest group of a bucket is never cleared and everyone else matches it
+      // one of the groups of a shared bucket arrived first and is not listed, so a suspect marks the HIGHER of
+      // every equal pair it finds; the lowest group of a bucket is never marked and everyone else is
       for (u32 i = threadIdx.x; i < nd; i += kScanThreads) {
         const int q = s_dupq[i];
         const uint2 rq = rng[q];
-        if (rq.x == rq.y) continue;  // already cleared by another suspect
         for (int p = 0; p < sB; ++p) {
           const uint2 rp = rng[p];  // non-empty buckets are equal iff their ranges are
-          if (p != q && rp.x == rq.x && rp.y == rq.y) rng[max(p, q)] = make_uint2(0u, 0u);
+          if (p != q && rp.x == rq.x && rp.y == rq.y) {
+            const int m = max(p, q);
+            atomicOr(&s_kill[m >> 5], 1u << (m & 31));
+          }
         }
       }
     } else {  // list overflow: every group looks for a lower group with the same bucket
@@ -425,12 +440,15 @@ eloc_scan_kernel(const u64 *__restrict__ bra, long long n, GroupView gv, HitRun 
         for (int p = 0; p < q; ++p) {
           const uint2 rp = rng[p];
           if (rp.x == rq.x && rp.y == rq.y) {
-            rng[q] = make_uint2(0u, 0u);
+            atomicOr(&s_kill[q >> 5], 1u << (q & 31));
             break;
           }
         }
       }
     }
+    __syncthreads();
+    for (int q = threadIdx.x; q < sB; q += kScanThreads)
+      if ((s_kill[q >> 5] >> (q & 31)) & 1u) rng[q] = make_uint2(0u, 0u);
     __syncthreads();
     for (int q0 = q_lo; q0 < q_hi; q0 += kScanThreads) {  // the work counts again
       const int q = q0 + (int)threadIdx.x;
