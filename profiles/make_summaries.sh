@@ -6,7 +6,7 @@ OUT=profiles/$TAG
 mkdir -p $OUT
 cp gpurun_out/${TAG}_launches.csv $OUT/launches.csv
 ( echo "ncu --metrics gpu__time_duration.sum --clock-control none: python bench.py --steps 2 --warmup 1 --no-cpu-baseline"
-  echo "(5 E_loc steps (1 warm-up, 2 timed, 2 end-to-end) of 1e6 samples = 4 batches of <= 262 144 samples each, then the API-path"
+  echo "(6 E_loc steps (1 warm-up, 2 timed, 1 end-to-end warm-up, 2 end-to-end) of 1e6 samples = 4 batches of <= 262 144 samples each, then the API-path"
   echo " chunk timings; per-launch times are cold-cache and serialised)"; echo
   python profiles/launch_summary.py $OUT/launches.csv 2>/dev/null | head -40 ) > $OUT/launches_summary.txt
 python profiles/ncu_summary.py gpurun_out/${TAG}_eloc.ncu-rep > $OUT/eloc_kernels_ncu.txt
