@@ -120,3 +120,53 @@ def test_exchange_and_statistics(world, overlap, cplx):
     for i in range(world):
         ends.append(ends[-1] + qq + (1 if i < rr else 0))
     assert covered == [(ends[i], ends[i + 1]) for i in range(world)]
+
+
+def _lut_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from pynqs_b200.distributed import build_shared_lut
+
+        keys = S.random_onvs(900, 40, 15, 15, seed=200)
+        psi = S.random_psi(900, seed=201)
+        cuts = [0, 250, 900]
+        sel = np.arange(cuts[rank], cuts[rank + 1])
+        counts = torch.from_numpy(np.arange(1, len(sel) + 1, dtype=np.int64))
+        x, prob, lut = build_shared_lut(torch.from_numpy(keys[sel]), torch.from_numpy(psi[sel]), 40, counts, disjoint=True)
+        q.put((rank, x.numpy(), prob.numpy(), lut.bra_key.numpy(), lut.wf_value.numpy(), lut.rank_begin, lut.rank_end))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_build_shared_lut_same_table_everywhere_and_slices_partition():
+    """build_shared_lut (the replacement of Sampler.gather_scatter_sample, vmc/sample.py:627-772): every rank ends
+    up with the same sorted table, the ranks' slices partition the merged unique set and prob carries the
+    reference's prob * world_size convention."""
+    from oracle import oracle as O
+
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_lut_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=180) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    keys = S.random_onvs(900, 40, 15, 15, seed=200)
+    psi = S.random_psi(900, seed=201)
+    order = O.sort_onv(keys)
+    cnt = np.concatenate([np.arange(1, 251), np.arange(1, 651)]).astype(np.float64)
+    xs, probs = [], []
+    for rank, x, prob, tab_keys, tab_psi, rb, re_ in res:
+        np.testing.assert_array_equal(tab_keys, keys[order])   # the reference's sorted order, identical on every rank
+        np.testing.assert_array_equal(tab_psi, psi[order])
+        assert (rb, re_) == ((0, 450) if rank == 0 else (450, 900))
+        xs.append(x)
+        probs.append(prob)
+    np.testing.assert_array_equal(np.concatenate(xs), keys)    # disjoint pieces: concatenation in rank order
+    np.testing.assert_allclose(np.concatenate(probs), cnt / cnt.sum() * world, rtol=1e-15)
