@@ -306,13 +306,9 @@ eloc_scan_kernel(const u64 *__restrict__ bra, long long n, GroupView gv, HitRun 
   if (s >= n) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   HitRun *my_run = runs + (s * splits + split) * kScanWarps + warp;
-  if (gv.hdr->has_dup) {  // duplicate keys: the eval kernel takes the reference's route for every sample
-    if (lane == 0) {
-      const HitRun run = {0u, kOverflow};
-      *my_run = run;
-    }
-    return;
-  }
+  // duplicate keys in the table: the eval kernel takes the reference's route for every sample.  The flag is
+  // loaded here and looked at only when the run record is written, so no CTA starts by waiting for it.
+  const u32 table_has_dup = __ldg(&gv.hdr->has_dup);
   const Onv<L> x = load_onv<L>(bra + s * L);
   // HALF: the beta singles are picked straight out of the folded beta string (n-th set bit); the orbital lists
   // are only built when a group has to be searched
@@ -616,7 +612,7 @@ eloc_scan_kernel(const u64 *__restrict__ bra, long long n, GroupView gv, HitRun 
   // publish this warp's hits (no CTA barrier: every warp owns its run record)
   __syncwarp();
   u32 off = 0;
-  bool over = qn > (u32)kQueue;
+  bool over = qn > (u32)kQueue || table_has_dup != 0u;
   if (lane == 0 && !over && qn) {
     off = atomicAdd(cursor, qn);
     if (off > hit_cap || qn > hit_cap - off) over = true;  // buffer exhausted
