@@ -52,7 +52,8 @@ def split_length_idx(dim: int, length: int) -> List[int]:
 
 class WavefunctionLUT:
     """Sorted key table + values with lookup; same constructor, attributes and return values as
-    the reference class.  On CUDA the lookups go through a device hash index built once here."""
+    the reference class.  On CUDA the table is sorted by the library (sort_table) and two device accelerators
+    are built on first use: a hash index behind lookup(), string-grouped copies behind the one-pass local energy."""
 
     def __init__(self, bra_key: Tensor, wf_value: Tensor, sorb: int, device=None, sort: bool = True,
                  rank: Optional[int] = None, world_size: Optional[int] = None) -> None:
