@@ -200,9 +200,53 @@ def main_reduce():
     save("reduce_fe2s2", **out)
 
 
+def main_simple():
+    """SIMPLE-method golden (vmc.energy.eloc._simple of the reference: every connected determinant goes through
+    the ansatz, via Func with and without a LUT) on the Fe2S2 integrals, toy ansatz."""
+    torch.set_num_threads(os.cpu_count())
+    ref = load_ref(1)
+    libs = types.ModuleType("libs")
+    libs.__path__ = []
+    sys.modules["libs"] = libs
+    sys.modules["libs.C_extension"] = ref
+    libs.C_extension = ref
+    sys.path.insert(0, REFERENCE)
+    from utils.public_function import WavefunctionLUT  # reference code
+    from vmc.energy.eloc import _simple  # reference code
+
+    d = torch.load(os.path.join(REFERENCE, "example/Fe2S2/fe2s2-OO.pth"), weights_only=False)
+    h1e, h2e = d["h1e"], d["h2e"]
+    ci = d["ci_space"].numpy()
+    sorb, noA, noB, nele = int(d["sorb"]), int(d["noa"]), int(d["nob"]), int(d["nele"])
+    first, n = 3000, 8
+    x = t(ci[first : first + n].copy())
+    out = dict(first=first, n=n)
+    for tag, cplx in (("real", False), ("complex", True)):
+        dtype = torch.complex128 if cplx else torch.double
+
+        def ansatz(states):
+            return toy_amplitude(states, sorb, cplx)
+
+        def batcher(x, func):
+            return func(ref.onv_to_tensor(x, sorb)).to(dtype)
+
+        eloc, _, psi_x, _ = _simple(x, h1e, h2e, ansatz, batcher, sorb, nele, noA, noB, dtype=dtype, WF_LUT=None, use_unique=True)
+        out[f"eloc_{tag}"] = eloc.numpy()
+        out[f"psi_x_{tag}"] = psi_x.numpy()
+        psi_tab = S.random_psi(ci.shape[0] // 2, seed=43, complex_=cplx)
+        lut = WavefunctionLUT(t(ci[::2].copy()), t(psi_tab).to(dtype), sorb, "cpu")
+        eloc, _, psi_x, _ = _simple(x, h1e, h2e, ansatz, batcher, sorb, nele, noA, noB, dtype=dtype, WF_LUT=lut, use_unique=True)
+        out[f"eloc_lut_{tag}"] = eloc.numpy()
+        out[f"psi_x_lut_{tag}"] = psi_x.numpy()
+    save("simple_fe2s2", **out)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "reduce":
         main_reduce()
+    elif len(sys.argv) > 1 and sys.argv[1] == "simple":
+        main_simple()
     else:
         main()
         main_reduce()
+        main_simple()
