@@ -1,21 +1,27 @@
 #!/usr/bin/env python
-"""bench.py -- E_loc samples/sec on the Fe2S2-shaped workload (BASELINE.json configs[1]).
+"""bench.py -- E_loc samples/sec on the Fe2S2 workload (BASELINE.json configs[1]).
 
     python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
     python bench.py --impl reference [...]                          # reference CPU build (oracle/_ref)
+    python bench.py --impl reference_cuda [...]                     # reference CUDA build (oracle/_ref, GPU-vs-GPU)
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
 
-Workload: 40 spin orbitals, 15 alpha + 15 beta electrons (M = 7876 connected determinants per
-sample), 10^6 unique seeded random ONVs that are both the evaluated samples and the lookup
-table, random 8-fold-symmetric integrals (seed 7), psi = randn (seed 1235), FP64.
+Workload: Fe2S2 CAS(30e,20o): 40 spin orbitals, 15 alpha + 15 beta electrons (M = 7876 connected determinants
+per sample), the reference's own Fe2S2 integrals (example/Fe2S2/fe2s2-OO.pth, shipped here as the data file
+tests/golden/fe2s2_integrals.npz), 10^6 unique seeded random ONVs that are both the evaluated samples and the
+lookup table, psi = randn (seed 1235), FP64.
 
 One step = one pass of the hot path over the whole sample set:
-  [N > 1: NCCL all-gather of every rank's unique ONVs + psi] -> sorted table + hash index ->
+  [N > 1: NCCL all-gather of every rank's unique ONVs + psi] -> sorted table + string-grouped copies ->
   one-pass sample-space E_loc on this rank's slice -> fused energy statistics (one collective).
-Strong scaling: the 10^6 samples are sharded over the ranks.  `value` = samples / step time with
-everything resident in HBM; `e2e` repeats the step from pinned HOST buffers (H2D of ONVs + psi,
-D2H of E_loc + statistics inside the timed region).  L2 is flushed between timed steps.
-Prints ONE JSON line on rank 0.
+Strong scaling: the 10^6 samples are sharded over the ranks.  `value` = samples / step time with everything
+resident in HBM; `e2e` repeats the step from pinned HOST buffers (H2D of ONVs + psi, D2H of E_loc + statistics
+inside the timed region).  L2 is flushed between timed steps.
+
+Parity is part of the line: the E_loc values the `cpu_baseline` leg computes with the unmodified reference
+extension (>= 10^5 samples of the same 10^6-key run) are compared with the GPU values of the same samples
+(`parity`); the run exits non-zero when they differ by more than 1e-12 relative / 1e-10 Ha on the mean.  The same
+is done for a complex128 psi and for a skewed (Zipf) table (`variants`).  Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
 
@@ -36,8 +42,10 @@ if ROOT not in sys.path:
 
 SORB, NOA, NOB = 40, 15, 15
 NELE = NOA + NOB
+M_FE2S2 = 7876
 METRIC = "E_loc samples/sec (Fe2S2 40 sorb)"
 UNIT = "samples/s"
+TOL_REL, TOL_MEAN_HA = 1e-12, 1e-10
 
 
 def algorithmic_bytes_per_sample(M: int, L: int, psi_bytes: int = 8) -> int:
@@ -55,13 +63,52 @@ def hbm_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def make_inputs(n_samples: int):
+# ---- inputs ------------------------------------------------------------------------------------------------------
+def load_integrals():
+    """The config-2 Hamiltonian: the reference's Fe2S2 integrals (data file made by tests/golden/make_golden.py)."""
     from pynqs_b200 import synthetic as S
 
-    keys = S.random_onvs(n_samples, SORB, NOA, NOB, seed=1234)
-    psi = S.random_psi(keys.shape[0], seed=1235)
+    path = os.path.join(ROOT, "tests", "golden", "fe2s2_integrals.npz")
+    if os.path.exists(path):
+        g = np.load(path)
+        assert int(g["sorb"]) == SORB and int(g["noA"]) == NOA and int(g["noB"]) == NOB
+        return np.ascontiguousarray(g["h1e"]), np.ascontiguousarray(g["h2e"]), "fe2s2-OO.pth of the reference (tests/golden/fe2s2_integrals.npz)"
     h1e, h2e = S.random_packed_integrals(SORB, seed=7, symmetric=True)
-    return keys, psi, h1e, h2e
+    return h1e, h2e, "random 8-fold symmetric, seed 7 (Fe2S2 data file missing)"
+
+
+def _strings(n, rng, shift=0):
+    occ = np.argsort(rng.random((n, SORB // 2)), axis=1)[:, :NOA]
+    out = np.zeros(n, dtype=np.uint64)
+    for c in range(NOA):
+        out |= np.uint64(1) << (2 * occ[:, c] + shift).astype(np.uint64)
+    return out
+
+
+def make_table(kind: str, n: int) -> np.ndarray:
+    """uint8 [n, 8] unique ONVs.  uniform: every determinant equally likely.  zipf0.8: the beta strings are drawn
+    with Zipf(0.8) weights over all C(20,15) strings, so the table is dominated by a few heavy strings (groups of
+    thousands of keys next to groups of a handful) like a VMC sample set."""
+    from pynqs_b200 import synthetic as S
+
+    if kind == "uniform":
+        return S.random_onvs(n, SORB, NOA, NOB, seed=1234)
+    if kind.startswith("zipf"):
+        beta_exp = float(kind[4:])
+        rng = np.random.default_rng(3)
+        beta = np.unique(_strings(400_000, rng))  # all 15504 strings with overwhelming probability
+        beta = beta[rng.permutation(beta.size)] << np.uint64(1)
+        w = 1.0 / np.arange(1, beta.size + 1) ** beta_exp
+        keys = np.unique(_strings(3 * n, rng) | beta[rng.choice(beta.size, size=3 * n, p=w / w.sum())])
+        keys = keys[rng.permutation(keys.size)[:n]]
+        return np.ascontiguousarray(keys.view(np.uint8).reshape(-1, 8))
+    raise ValueError(kind)
+
+
+def make_psi(n: int, cplx: bool) -> np.ndarray:
+    from pynqs_b200 import synthetic as S
+
+    return S.random_psi(n, seed=1235, complex_=cplx)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -112,37 +159,46 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax), "reasons": sorted(reasons), "samples": len(sm)}
 
 
-# ------------------------------------------------------------------------------------------------
-def reference_ops():
+# ---- the reference arms ---------------------------------------------------------------------------------------------
+def reference_ops(cuda: bool = False):
     """(module, kind): the unmodified reference extension if oracle/_ref was built, else the oracle port."""
     from oracle import build_ref
 
+    if cuda:
+        return (build_ref.load_ref(1, cuda=True), "reference_cuda") if build_ref.cuda_available(1) else (None, "unavailable")
     if build_ref.available(1):
         return build_ref.load_ref(1), "reference"
     return None, "port"
 
 
+def reference_eloc_step(ref, x, h1e, h2e, key, val):
+    """The reference's op sequence for the sample-space local energy (vmc/energy/eloc.py:369-397) on torch tensors
+    of either device, through the reference extension `ref`."""
+    import torch
+
+    comb_x, comb_hij = ref.get_comb_hij_fused(x, h1e, h2e, SORB, NELE, NOA, NOB)
+    x1 = comb_x.reshape(-1, comb_x.size(2))
+    psi_x1 = torch.zeros(x.size(0), comb_x.size(1), dtype=val.dtype, device=x.device)
+    idx_array, mask = ref.wavefunction_lut(key, x1, SORB)
+    baseline = torch.arange(x1.size(0), dtype=torch.int64, device=x.device)
+    psi_x1.view(-1)[baseline[mask]] = val[idx_array.masked_select(mask)]
+    return ((psi_x1.T / psi_x1[..., 0]).T * comb_hij).sum(-1)
+
+
 def cpu_eloc_step(ref, kind, x_np, h1e_np, h2e_np, skeys_np, spsi_np):
-    """Reference op sequence of vmc/energy/eloc.py:369-397 on the host. Returns eloc (numpy)."""
     import torch
 
     if kind == "reference":
-        x, h1e, h2e = torch.from_numpy(x_np), torch.from_numpy(h1e_np), torch.from_numpy(h2e_np)
-        key, val = torch.from_numpy(skeys_np), torch.from_numpy(spsi_np)
-        comb_x, comb_hij = ref.get_comb_hij_fused(x, h1e, h2e, SORB, NELE, NOA, NOB)
-        x1 = comb_x.reshape(-1, comb_x.size(2))
-        psi_x1 = torch.zeros(x.size(0), comb_x.size(1), dtype=val.dtype)
-        idx_array, mask = ref.wavefunction_lut(key, x1, SORB)
-        baseline = torch.arange(x1.size(0), dtype=torch.int64)
-        psi_x1.view(-1)[baseline[mask]] = val[idx_array.masked_select(mask)]
-        return ((psi_x1.T / psi_x1[..., 0]).T * comb_hij).sum(-1).numpy()
+        t = torch.from_numpy
+        return reference_eloc_step(ref, t(x_np), t(h1e_np), t(h2e_np), t(skeys_np), t(spsi_np)).numpy()
     from oracle import oracle as O
 
     return O.eloc_sample_space(x_np, h1e_np, h2e_np, skeys_np, spsi_np, SORB, NELE, NOA, NOB)
 
 
-def time_cpu_baseline(keys, psi, h1e, h2e, budget_s=12.0, chunk=512):
-    """Bounded sample of the same workload on the host cores: E_loc of `m` samples against the full table."""
+def cpu_reference_eloc(keys, psi, h1e, h2e, budget_s=12.0, chunk=512, max_samples=None):
+    """Bounded sample of the same workload on the host cores: E_loc of the first `done` samples (original order)
+    against the full table.  Returns (eloc[done], record)."""
     import torch
 
     from oracle import oracle as O
@@ -155,16 +211,36 @@ def time_cpu_baseline(keys, psi, h1e, h2e, budget_s=12.0, chunk=512):
     if kind == "port":
         chunk = 32
     cpu_eloc_step(ref, kind, keys[:chunk], h1e, h2e, skeys, spsi)  # warm-up
-    done, t0 = 0, time.perf_counter()
+    out, done, t0 = [], 0, time.perf_counter()
     while True:
-        cpu_eloc_step(ref, kind, keys[done : done + chunk], h1e, h2e, skeys, spsi)
+        out.append(cpu_eloc_step(ref, kind, keys[done : done + chunk], h1e, h2e, skeys, spsi))
         done += chunk
         el = time.perf_counter() - t0
-        if el > budget_s or done + chunk > keys.shape[0]:
+        if el > budget_s or done + chunk > keys.shape[0] or (max_samples is not None and done >= max_samples):
             break
-    return {"value": done / el, "unit": UNIT, "cores": cores, "kind": kind,
-            "sample": f"{done} of {keys.shape[0]} samples in {chunk}-sample chunks against the full {keys.shape[0]}-key table "
-                      f"(get_comb_hij_fused + wavefunction_lut + torch reduce), {el:.1f} s"}
+    rec = {"value": done / el, "unit": UNIT, "cores": cores, "kind": kind,
+           "sample": f"{done} of {keys.shape[0]} samples in {chunk}-sample chunks against the full {keys.shape[0]}-key table "
+                     f"(get_comb_hij_fused + wavefunction_lut + torch reduce), {el:.1f} s"}
+    return np.concatenate(out), rec
+
+
+def parity_block(eloc_gpu_orig: np.ndarray, eloc_ref: np.ndarray, psi: np.ndarray, against: str) -> dict:
+    """GPU E_loc vs reference E_loc of the same samples: per-element relative error and the |psi|^2-weighted mean."""
+    n = eloc_ref.shape[0]
+    a, b = eloc_gpu_orig[:n], eloc_ref
+    rel = np.abs(a - b) / np.abs(b)
+    w = np.abs(psi[:n]) ** 2
+    w = w / w.sum()
+    mean_a, mean_b = complex(np.sum(w * a)), complex(np.sum(w * b))
+    diff = abs(mean_a - mean_b)
+    ok = bool(np.all(np.isfinite(a)) and rel.max() <= TOL_REL and diff <= TOL_MEAN_HA)
+    return {"n": int(n), "against": against, "max_rel_err": float(rel.max()), "mean_energy_abs_diff_ha": float(diff),
+            "mean_energy_ha": mean_b.real, "tol_rel": TOL_REL, "tol_mean_ha": TOL_MEAN_HA, "ok": ok}
+
+
+def base_config(n_total: int, integrals: str, table: str = "uniform") -> dict:
+    return {"workload": "fe2s2_cas30e20o_40sorb_15a15b", "sorb": SORB, "noA": NOA, "noB": NOB, "M": M_FE2S2, "n_samples": int(n_total),
+            "lut_keys": int(n_total), "integrals": integrals, "table": table}
 
 
 def run_reference_arm(args):
@@ -175,20 +251,37 @@ def run_reference_arm(args):
 
     from oracle import oracle as O
 
-    keys, psi, h1e, h2e = make_inputs(args.samples)
-    ref, kind = reference_ops()
+    cuda = args.impl == "reference_cuda"
+    keys = make_table("uniform", args.samples)
+    psi = make_psi(keys.shape[0], False)
+    h1e, h2e, integrals = load_integrals()
+    ref, kind = reference_ops(cuda)
+    if cuda and (ref is None or not torch.cuda.is_available()):
+        print(json.dumps({"impl": "reference_cuda", "unavailable": "oracle/_ref/C_extension_cuda_L1.so missing or no CUDA device"}), flush=True)
+        return
     cores = os.cpu_count() if kind == "reference" else 1
-    torch.set_num_threads(cores)
+    torch.set_num_threads(os.cpu_count())
     order = O.sort_onv(keys)
     skeys, spsi = np.ascontiguousarray(keys[order]), np.ascontiguousarray(psi[order])
-    per_step = args.ref_samples if kind == "reference" else 64
-    chunk = 512 if kind == "reference" else 32
-    M = 7876
+    if cuda:
+        per_step, chunk = 32768, 8192
+        dev = torch.device("cuda", 0)
+        d = lambda a: torch.from_numpy(a).to(dev)  # noqa: E731
+        d_keys, d_h1e, d_h2e, d_skeys, d_spsi = d(keys), d(h1e), d(h2e), d(skeys), d(spsi)
 
-    def step(i):
-        lo = (i * per_step) % (keys.shape[0] - per_step)
-        for b in range(lo, lo + per_step, chunk):
-            cpu_eloc_step(ref, kind, keys[b : min(b + chunk, lo + per_step)], h1e, h2e, skeys, spsi)
+        def step(i):
+            lo = (i * per_step) % (keys.shape[0] - per_step)
+            for b in range(lo, lo + per_step, chunk):
+                reference_eloc_step(ref, d_keys[b : b + chunk], d_h1e, d_h2e, d_skeys, d_spsi)
+            torch.cuda.synchronize()
+    else:
+        per_step = args.ref_samples if kind == "reference" else 64
+        chunk = 512 if kind == "reference" else 32
+
+        def step(i):
+            lo = (i * per_step) % (keys.shape[0] - per_step)
+            for b in range(lo, lo + per_step, chunk):
+                cpu_eloc_step(ref, kind, keys[b : min(b + chunk, lo + per_step)], h1e, h2e, skeys, spsi)
 
     for i in range(args.warmup):
         step(i)
@@ -200,11 +293,10 @@ def run_reference_arm(args):
     sample = (f"each step = E_loc of {per_step} samples ({chunk}-sample chunks) against the prebuilt sorted "
               f"{keys.shape[0]}-key table; table sort not timed")
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "impl": args.impl, "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "fe2s2_cas30e20o_40sorb_15a15b", "sorb": SORB, "noA": NOA, "noB": NOB, "M": M,
-                   "n_samples": int(keys.shape[0]), "lut_keys": int(keys.shape[0]), "integrals": "random 8-fold symmetric, seed 7"},
+        "config": base_config(keys.shape[0], integrals),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -234,174 +326,212 @@ def run_ours(args):
     from pynqs_b200.lut import WavefunctionLUT, split_length_idx
 
     _lib.load()
-    keys_np, psi_np, h1e_np, h2e_np = make_inputs(args.samples)
-    n_total = keys_np.shape[0]
-    M = ops.get_Num_SinglesDoubles(SORB, NOA, NOB) + 1
-    # every rank "samples" a contiguous piece of the unique set (disjoint pieces, like use_same_tree)
-    cuts = [0] + split_length_idx(n_total, world)
-    lo, hi = cuts[rank], cuts[rank + 1]
-    host_keys = torch.from_numpy(keys_np[lo:hi]).pin_memory()
-    host_psi = torch.from_numpy(psi_np[lo:hi]).pin_memory()
-    d_keys, d_psi = host_keys.to(dev), host_psi.to(dev)
+    h1e_np, h2e_np, integrals = load_integrals()
     h1e, h2e = torch.from_numpy(h1e_np).to(dev), torch.from_numpy(h2e_np).to(dev)
+    M = ops.get_Num_SinglesDoubles(SORB, NOA, NOB) + 1
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
-    host_eloc = torch.empty(hi - lo + 1, dtype=torch.float64).pin_memory()
 
-    kern_ms, phase_ev = [], []
-    equal_sizes = n_total % world == 0
+    def measure(keys_np, psi_np, steps, warmup, want_e2e=True):
+        """Times `steps` steps of the hot path over the sample set (keys_np, psi_np); returns a dict of the
+        timings plus this rank's E_loc of the last step (device tensor, sorted-table order) and the sort permutation."""
+        n_total = keys_np.shape[0]
+        cplx = np.iscomplexobj(psi_np)
+        # every rank "samples" a contiguous piece of the unique set (disjoint pieces, like use_same_tree)
+        cuts = [0] + split_length_idx(n_total, world)
+        lo, hi = cuts[rank], cuts[rank + 1]
+        host_keys = torch.from_numpy(keys_np[lo:hi]).pin_memory()
+        host_psi = torch.from_numpy(psi_np[lo:hi]).pin_memory()
+        d_keys, d_psi = host_keys.to(dev), host_psi.to(dev)
+        host_eloc = torch.empty(hi - lo + 1, dtype=d_psi.dtype).pin_memory()
+        kern_ms, phase_ev, keep = [], [], {}
+        equal_sizes = n_total % world == 0
 
-    def step(from_host: bool):
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
-        ev[0].record()
-        if from_host:
-            k = host_keys.to(dev, non_blocking=True)
-            p = host_psi.to(dev, non_blocking=True)
-        else:
-            k, p = d_keys, d_psi
-        uniq, wf, cnt = exchange_unique_samples(k, p, None, disjoint=True, equal_sizes=equal_sizes)
-        ev[1].record()
-        lut = WavefunctionLUT(uniq, wf, SORB, dev, rank=rank, world_size=world)
-        gidx = lut.group_index  # built here, inside the table phase
-        b, e = rank_slice(uniq.size(0), rank, world)
-        x = uniq[b:e]
-        e0, e1 = ev[2], ev[3]
-        e0.record()
-        eloc, psi0 = ops.eloc_sample_space(x, h1e, h2e, SORB, NELE, NOA, NOB, lut.bra_key, lut.wf_value, gidx)
-        e1.record()
-        # p_i = |psi_i|^2 / sum_table |psi|^2 * world (reference convention, sample.py:772); the ranks' slices
-        # partition the table, so the norm comes out of the statistics' own all-gather
-        st = energy_statistics_amplitudes(eloc, psi0)
-        if from_host:
-            host_eloc[: e - b].copy_(eloc, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-        ev[4].record()
-        kern_ms.append((e0, e1, e - b))
-        if not from_host:
-            phase_ev.append(ev)
-        return st
+        def step(from_host: bool):
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+            ev[0].record()
+            if from_host:
+                k = host_keys.to(dev, non_blocking=True)
+                p = host_psi.to(dev, non_blocking=True)
+            else:
+                k, p = d_keys, d_psi
+            uniq, wf, cnt = exchange_unique_samples(k, p, None, disjoint=True, equal_sizes=equal_sizes)
+            ev[1].record()
+            lut = WavefunctionLUT(uniq, wf, SORB, dev, rank=rank, world_size=world)
+            gidx = lut.group_index  # built here, inside the table phase
+            b, e = rank_slice(uniq.size(0), rank, world)
+            x = uniq[b:e]
+            e0, e1 = ev[2], ev[3]
+            e0.record()
+            eloc, psi0 = ops.eloc_sample_space(x, h1e, h2e, SORB, NELE, NOA, NOB, lut.bra_key, lut.wf_value, gidx)
+            e1.record()
+            # p_i = |psi_i|^2 / sum_table |psi|^2 * world (reference convention, sample.py:772); the ranks' slices
+            # partition the table, so the norm comes out of the statistics' own collective
+            # (the collective is issued inside the step; the host read of its 7 doubles per rank happens after the
+            #  timed region -- except end to end, where reading the result back IS part of the step)
+            st = energy_statistics_amplitudes(eloc, psi0, lazy=True)
+            if from_host:
+                host_eloc[: e - b].copy_(eloc, non_blocking=True)
+                st = st.result()
+            ev[4].record()
+            kern_ms.append((e0, e1, e - b))
+            if not from_host:
+                phase_ev.append(ev)
+            keep["eloc"], keep["x"], keep["lut"] = eloc, x, lut
+            return st
 
-    def timed(n_steps: int, from_host: bool):
-        total_ms = 0.0
-        for _ in range(n_steps):
-            flush.fill_(1)  # write > L2 (126 MB) between timed steps
-            torch.cuda.synchronize()
+        def timed(n_steps: int, from_host: bool):
+            total_ms = 0.0
+            st = None
+            for _ in range(n_steps):
+                flush.fill_(1)  # write > L2 (126 MB) between timed steps
+                torch.cuda.synchronize()
+                if world > 1:
+                    dist.barrier()
+                s, t = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s.record()
+                st = step(from_host)
+                t.record()
+                torch.cuda.synchronize()
+                total_ms += s.elapsed_time(t)
+            tt = torch.tensor([total_ms], dtype=torch.float64, device=dev)
             if world > 1:
-                dist.barrier()
-            s, t = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s.record()
-            st = step(from_host)
-            t.record()
-            torch.cuda.synchronize()
-            total_ms += s.elapsed_time(t)
-        tt = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        return float(tt.item()), st
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            return float(tt.item()), st
 
-    for _ in range(args.warmup):
-        step(False)
-    torch.cuda.synchronize()
-    kern_ms.clear()
-    phase_ev.clear()
+        for _ in range(warmup):
+            step(False)
+        torch.cuda.synchronize()
+        kern_ms.clear()
+        phase_ev.clear()
+        l0 = _lib.launch_count()
+        total_ms, st = timed(steps, False)
+        launches = _lib.launch_count() - l0
+        kern = [(a.elapsed_time(b), n) for a, b, n in kern_ms]
+        out = {"n_total": n_total, "ms_per_step": total_ms / steps, "value": n_total / (total_ms / steps * 1e-3), "launches": int(launches),
+               "kernel_ms": sum(t for t, _ in kern) / len(kern), "kernel_samples": kern[0][1], "stats": st.result() if hasattr(st, "result") else st,
+               "cplx": cplx}
+        names = ["exchange", "table_sort_and_index", "eloc_kernels", "probabilities_and_statistics"]
+        out["phases"] = {nm: sum(ev[i].elapsed_time(ev[i + 1]) for ev in phase_ev) / len(phase_ev) for i, nm in enumerate(names)}
+        if want_e2e:
+            for _ in range(min(warmup, 2)):  # the end-to-end path has first-use costs of its own (pinned copies both ways)
+                step(True)
+            torch.cuda.synchronize()
+            e2e_ms, st2 = timed(steps, True)
+            st2 = st2.result() if hasattr(st2, "result") else st2
+            out["e2e"] = {"value": n_total / (e2e_ms / steps * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(n_total * (8 + d_psi.element_size())),
+                          "d2h_bytes_per_step": int(n_total * d_psi.element_size() + 40 * world), "ms_per_step": e2e_ms / steps}
+            out["mean_e2e"] = st2["mean"]
+        # E_loc of this rank's slice back in the ORIGINAL sample order (rank 0 at N = 1 only: parity legs)
+        if world == 1:
+            lut = keep["lut"]
+            eloc_orig = torch.empty_like(keep["eloc"])
+            eloc_orig[lut._sort_perm] = keep["eloc"]
+            out["eloc_orig"] = eloc_orig.cpu().numpy()
+        out["d_keys"], out["d_psi"] = d_keys, d_psi
+        return out
+
+    keys_np = make_table("uniform", args.samples)
+    psi_np = make_psi(keys_np.shape[0], False)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    l0 = _lib.launch_count()
-    total_ms, st = timed(args.steps, False)
-    launches = _lib.launch_count() - l0
-    kern = [(a.elapsed_time(b), n) for a, b, n in kern_ms]
-    for _ in range(min(args.warmup, 2)):  # the end-to-end path has first-use costs of its own (pinned copies both ways)
-        step(True)
-    torch.cuda.synchronize()
-    e2e_ms, st2 = timed(args.steps, True)
-    names = ["exchange", "table_sort_and_index", "eloc_kernels", "probabilities_and_statistics"]
-    phases = {nm: sum(ev[i].elapsed_time(ev[i + 1]) for ev in phase_ev) / len(phase_ev) for i, nm in enumerate(names)}
+    main = measure(keys_np, psi_np, args.steps, args.warmup)
     clocks = sampler.stop() if rank == 0 else None
+    n_total = main["n_total"]
 
-    ms_per_step = total_ms / args.steps
-    value = n_total / (ms_per_step * 1e-3)
-    e2e_value = n_total / (e2e_ms / args.steps * 1e-3)
+    # variants (shorter runs of the same step): complex128 psi (config 2 is complex, Fe2S2-OO-dcut-20.py:39) and a skewed table
+    variants = {}
+    vsteps, vwarm = max(3, min(args.steps, 5)), 3
+    if not args.no_variants and world == 1:
+        psi_c = make_psi(n_total, True)
+        variants["complex128"] = (measure(keys_np, psi_c, vsteps, vwarm, want_e2e=False), keys_np, psi_c)
+        keys_z = make_table("zipf0.8", args.samples)
+        variants["zipf0.8"] = (measure(keys_z, psi_np[: keys_z.shape[0]], vsteps, vwarm, want_e2e=False), keys_z, psi_np[: keys_z.shape[0]])
+
     B = algorithmic_bytes_per_sample(M, 1)
-    k_ms = sum(t for t, _ in kern) / len(kern)
-    k_n = kern[0][1]
     peak, peak_src = hbm_peak_gbs()
-    achieved = B * k_n / (k_ms * 1e-3) / 1e9
     prof = load_profile_numbers()
-    per_sample_dram = prof.get("eloc_dram_bytes_per_sample")
-    roof = {"bound": "hbm", "kernel": "eloc_scan_kernel<1,folded,128> (+ eloc_eval_kernel, diag_kernel): one-pass sample-space E_loc",
-            "launch": "one pynqs_eloc_sample_space call on this rank's samples = 1 diag kernel + one scan and one eval kernel per batch of <= 262 144 samples",
-            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": per_sample_dram * k_n if per_sample_dram else None,
-            "traffic_note": "DRAM bytes per call from ncu (profiles/r01/traffic.json: %s B/sample): the table copies stay in L2" % per_sample_dram,
-            "peak_source": peak_src, "algorithmic_bytes_per_sample": B, "algorithmic_bytes_per_launch": B * k_n,
+    k_ms, k_n = main["kernel_ms"], main["kernel_samples"]
+    equiv = B * k_n / (k_ms * 1e-3) / 1e9
+    inst = prof.get("eloc_warp_instructions_per_sample")
+    sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+    issue_peak = 148 * 4 * sm_mhz * 1e6  # warp-instructions / s: 4 schedulers per SM, one instruction per cycle each
+    issue_rate = inst * k_n / (k_ms * 1e-3) if inst else None
+    roof = {"bound": "issue",
+            "kernel": "one-pass sample-space E_loc: eloc scan kernels (+ eloc_eval_kernel, diag_table_kernel)",
+            "launch": "one pynqs_eloc_sample_space call on this rank's samples",
+            "achieved": issue_rate, "peak": issue_peak, "unit": "warp-instructions/s", "frac": issue_rate / issue_peak if issue_rate else None,
+            "achieved_note": "warp-instructions per sample from the committed ncu capture (profiles/%s) x samples per call / live CUDA-event time of the call; "
+                             "peak = 592 warp schedulers x sampled SM clock" % prof.get("tag", "?"),
+            "traffic": prof.get("eloc_dram_bytes_per_sample") and prof["eloc_dram_bytes_per_sample"] * k_n,
+            "traffic_note": "DRAM bytes per call from ncu (profiles/%s/traffic.json): the table copies stay in L2" % prof.get("tag", "?"),
             "samples_per_launch": k_n, "kernel_ms": k_ms,
-            "real_bound": {"what": "issue slots of eloc_scan_kernel (ncu, profiles/r01/eloc_kernels_ncu.txt, 262 144 samples per launch)",
-                           **prof.get("scan_kernel_ncu", {})},
-            "note": "equivalent-bytes roofline per SURVEY.md 8(d): the one-pass kernels never write comb/Hmat/idx, so "
-                    "'achieved' = API-path bytes (fused + lut, 259.9 KB/sample) / time and exceeds the HBM peak; they scan the "
-                    "string-grouped table copies out of L2 and their real bound is the issue slots (profiles/). The kernels "
-                    "that really move the API-path bytes are in 'roofline_hbm_kernels'."}
+            "equivalent_hbm": {"achieved": equiv, "peak": peak, "unit": "GB/s", "frac": equiv / peak, "peak_source": peak_src,
+                               "algorithmic_bytes_per_sample": B,
+                               "note": "SURVEY.md 8(d) equivalent-bytes figure: API-path bytes (fused + lut, 259.9 KB/sample) / time. NOT a physical HBM "
+                                       "fraction -- the one-pass kernels never write comb/Hmat/idx; the kernels that really move those bytes are in "
+                                       "'roofline_hbm_kernels'"}}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
+    cfg = base_config(n_total, integrals)
+    cfg.update({"method": "sample-space, one-pass kernels", "l2": "flushed between timed steps (512 MiB write)",
+                "parallelism": f"samples sharded over {world} rank(s)", "step": "exchange + table sort + grouped table + E_loc + statistics"})
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic",
-        "config": {"workload": "fe2s2_cas30e20o_40sorb_15a15b", "sorb": SORB, "noA": NOA, "noB": NOB, "M": M, "n_samples": n_total,
-                   "lut_keys": n_total, "integrals": "random 8-fold symmetric, seed 7", "method": "sample-space, one-pass kernels (group scan)",
-                   "l2": "flushed between timed steps (512 MiB write)", "parallelism": f"samples sharded over {world} rank(s)",
-                   "step": "exchange + table sort + grouped table + E_loc + statistics"},
-        "roofline": roof,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n_total * 16), "d2h_bytes_per_step": int(n_total * 8 + 40 * world),
-                "ms_per_step": e2e_ms / args.steps},
-        "gpu_launches": int(launches),
-        "phases_ms_rank0": phases,
-        "clocks": clocks,
-        "energy": {"mean": st["mean"], "var": st["var"], "mean_e2e": st2["mean"]},
+        "metric": METRIC, "value": main["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": cfg, "roofline": roof, "e2e": main["e2e"], "gpu_launches": main["launches"],
+        "phases_ms_rank0": main["phases"], "clocks": clocks,
+        "energy": {"mean": main["stats"]["mean"], "var": main["stats"]["var"], "mean_e2e": main["mean_e2e"]},
     }
-    if world == 1 and not args.no_api_path:
-        line["roofline_hbm_kernels"] = time_api_path(ops, dev, d_keys, d_psi, h1e, h2e, M, peak, prof)
+    ok = True
     if world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = time_cpu_baseline(keys_np, psi_np, h1e_np, h2e_np)
+        eloc_ref, rec = cpu_reference_eloc(keys_np, psi_np, h1e_np, h2e_np, budget_s=args.cpu_budget)
+        line["cpu_baseline"] = rec
+        line["parity"] = parity_block(main["eloc_orig"], eloc_ref, psi_np, f"unmodified reference extension ({rec['kind']}), same inputs")
+        ok &= line["parity"]["ok"]
     else:
         line["cpu_baseline"] = None
+    vout = {}
+    for name, (m, k_np, p_np) in variants.items():
+        ent = {"value": m["value"], "unit": UNIT, "ms_per_step": m["ms_per_step"], "steps": vsteps, "phases_ms_rank0": m["phases"],
+               "energy_mean": str(m["stats"]["mean"])}
+        if world == 1 and not args.no_cpu_baseline:
+            eloc_ref, rec = cpu_reference_eloc(k_np, p_np, h1e_np, h2e_np, budget_s=3.0, max_samples=args.variant_parity_samples)
+            ent["parity"] = parity_block(m["eloc_orig"], eloc_ref, p_np, f"unmodified reference extension ({rec['kind']}), same inputs")
+            ok &= ent["parity"]["ok"]
+        vout[name] = ent
+    if vout:
+        line["variants"] = vout
+    if world == 1 and not args.no_api_path:
+        line["roofline_hbm_kernels"] = time_api_path(ops, dev, main["d_keys"], main["d_psi"], h1e, h2e, M, peak, prof)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+    if not ok:
+        sys.stderr.write("bench.py: PARITY FAILURE against the reference extension (see 'parity' in the JSON line)\n")
+        sys.exit(3)
 
 
 def load_profile_numbers():
-    """ncu-derived numbers of the committed profile (profiles/r01/): per-launch DRAM traffic and, for the scan
-    kernel, the utilisation figures that say what really bounds it."""
-    out = {}
-    try:
-        out = json.load(open(os.path.join(ROOT, "profiles", "r01", "traffic.json")))
-    except Exception:
-        pass
-    try:
-        want = {"smsp__issue_active.avg.pct_of_peak_sustained_active": "issue_slots_busy_pct",
-                "lts__throughput.avg.pct_of_peak_sustained_elapsed": "l2_throughput_pct",
-                "dram__throughput.avg.pct_of_peak_sustained_elapsed": "dram_throughput_pct",
-                "sm__warps_active.avg.pct_of_peak_sustained_active": "occupancy_pct",
-                "gpu__time_duration.sum": "launch_us"}
-        scan = {}
-        for line in open(os.path.join(ROOT, "profiles", "r01", "eloc_kernels_ncu.txt")):
-            f = line.split()
-            if line.startswith("Kernel Name") and scan:
-                break  # first kernel of the report = eloc_scan_kernel
-            if f and f[0] in want:
-                scan[want[f[0]]] = float(f[1])
-        out["scan_kernel_ncu"] = scan
-    except Exception:
-        pass
-    return out
+    """ncu-derived numbers of the latest committed profile (profiles/rNN/traffic.json): per-launch DRAM traffic and
+    warp-instructions per sample of the one-pass kernels."""
+    for tag in ("r02", "r01"):
+        try:
+            out = json.load(open(os.path.join(ROOT, "profiles", tag, "traffic.json")))
+            out["tag"] = tag
+            out.setdefault("eloc_warp_instructions_per_sample", 5685 if tag == "r01" else None)
+            return out
+        except Exception:
+            continue
+    return {}
 
 
 def time_api_path(ops, dev, d_keys, d_psi, h1e, h2e, M, peak, prof, chunk=32768, reps=7):
-    """The materialising reference-API kernels on one chunk: the real HBM movers of the hot path.
-    Outputs are pre-allocated by torch inside the call (caching allocator, no cudaMalloc after warm-up);
+    """The materialising reference-API kernels on one chunk: the real HBM movers of the hot path, with the
+    UNMODIFIED reference CUDA extension (oracle/_ref/C_extension_cuda_L1.so) timed on the same tensors beside them.
+    Outputs are allocated by torch inside the call (caching allocator, no cudaMalloc after warm-up);
     2.06 GB comb + 2.06 GB Hmat per call exceed L2, so no flush is needed between repetitions."""
     import torch
 
@@ -411,7 +541,7 @@ def time_api_path(ops, dev, d_keys, d_psi, h1e, h2e, M, peak, prof, chunk=32768,
     x = lut.bra_key[:chunk]
     prep = ops.PreparedIntegrals(h2e, SORB)
 
-    def t(fn):
+    def t(fn, reps=reps):
         for _ in range(3):
             out = fn()
         ts = []
@@ -426,11 +556,29 @@ def time_api_path(ops, dev, d_keys, d_psi, h1e, h2e, M, peak, prof, chunk=32768,
 
     f_ms, (comb, hmat) = t(lambda: ops.get_comb_hij_fused(x, h1e, h2e, SORB, NELE, NOA, NOB, prepared=prep))
     flat = comb.view(-1, 8)
-    l_ms, _ = t(lambda: ops.wavefunction_lut(lut.bra_key, flat, SORB, hash_index=lut.hash_index))
+    l_ms, (idx, mask) = t(lambda: ops.wavefunction_lut(lut.bra_key, flat, SORB, hash_index=lut.hash_index))
     fb, lb = (16 * M + 8) * chunk, 17 * M * chunk
+    ref_cuda = {}
+    try:
+        ref, kind = reference_ops(cuda=True)
+        if ref is not None:
+            rf_ms, (rcomb, rhmat) = t(lambda: ref.get_comb_hij_fused(x, h1e, h2e, SORB, NELE, NOA, NOB), reps=3)
+            same_f = bool(torch.equal(rcomb, comb) and torch.equal(rhmat.view(torch.int64), hmat.view(torch.int64)))
+            del rcomb, rhmat
+            rl_ms, (ridx, rmask) = t(lambda: ref.wavefunction_lut(lut.bra_key, flat, SORB), reps=3)
+            same_l = bool(torch.equal(ridx, idx) and torch.equal(rmask, mask))
+            del ridx, rmask
+            ref_cuda = {"fused": {"ms": rf_ms, "speedup": rf_ms / f_ms, "bit_identical_outputs": same_f},
+                        "lut": {"ms": rl_ms, "speedup": rl_ms / l_ms, "bit_identical_outputs": same_l}}
+            sub = 8192
+            re_ms, _ = t(lambda: reference_eloc_step(ref, x[:sub], h1e, h2e, lut.bra_key, lut.wf_value), reps=3)
+            ref_cuda["eloc_three_call"] = {"ms": re_ms, "samples": sub, "samples_per_s": sub / re_ms * 1e3,
+                                           "what": "reference CUDA extension: get_comb_hij_fused + wavefunction_lut + torch scatter/divide/sum"}
+    except Exception as e:  # the comparator is optional: never fail the bench on it
+        ref_cuda = {"unavailable": repr(e)[:200]}
     # REDUCE method: kept rows only; eps at the 90th percentile of |H| of the first samples
     eps = float(torch.quantile(hmat[:64].abs().flatten()[:: 7], 0.9))
-    del comb, hmat, flat
+    del comb, hmat, flat, idx, mask
     r_ms, (xk, hk, ik, off) = t(lambda: ops.get_comb_hij_reduced(x, h1e, h2e, SORB, NELE, NOA, NOB, eps, prepared=prep))
     kept = int(ik.numel())
     rb = kept * (8 + 8 + 8) + 8 * (chunk + 1)
@@ -442,11 +590,14 @@ def time_api_path(ops, dev, d_keys, d_psi, h1e, h2e, M, peak, prof, chunk=32768,
     return [
         {"bound": "hbm", "kernel": "enumerate_kernel<1,double,true> (+diag_kernel) = get_comb_hij_fused", "achieved": fb / f_ms / 1e6,
          "peak": peak, "unit": "GB/s", "frac": fb / f_ms / 1e6 / peak, "traffic": prof.get("enumerate_dram_bytes_per_launch"),
-         "algorithmic_bytes_per_launch": fb, "samples_per_launch": chunk, "ms": f_ms, "samples_per_s": chunk / f_ms * 1e3},
+         "algorithmic_bytes_per_launch": fb, "samples_per_launch": chunk, "ms": f_ms, "samples_per_s": chunk / f_ms * 1e3,
+         "vs_reference_cuda": ref_cuda.get("fused", ref_cuda)},
         {"bound": "hbm", "kernel": "lut_indexed_kernel<1> = wavefunction_lut", "achieved": lb / l_ms / 1e6, "peak": peak,
          "unit": "GB/s", "frac": lb / l_ms / 1e6 / peak, "traffic": prof.get("lut_dram_bytes_per_launch"),
-         "algorithmic_bytes_per_launch": lb, "samples_per_launch": chunk, "ms": l_ms, "samples_per_s": chunk / l_ms * 1e3},
+         "algorithmic_bytes_per_launch": lb, "samples_per_launch": chunk, "ms": l_ms, "samples_per_s": chunk / l_ms * 1e3,
+         "vs_reference_cuda": ref_cuda.get("lut", ref_cuda)},
         reduce_entry,
+        {"kernel": "reference CUDA three-call E_loc (GPU-vs-GPU comparator of the headline value)", **ref_cuda.get("eloc_three_call", ref_cuda)},
     ]
 
 
@@ -455,13 +606,16 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference_cuda"])
     ap.add_argument("--samples", type=int, default=1_000_000)
     ap.add_argument("--ref-samples", type=int, default=4096, help="samples per step of the reference CPU arm")
+    ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of reference CPU work behind cpu_baseline / parity")
+    ap.add_argument("--variant-parity-samples", type=int, default=8192)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-api-path", action="store_true")
+    ap.add_argument("--no-variants", action="store_true")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.impl != "ours":
         run_reference_arm(args)
     else:
         run_ours(args)

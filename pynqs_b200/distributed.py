@@ -9,7 +9,8 @@ a barrier, utils/distributed/comm.py:56-67) by
      the merged tensors -- no pack / unpack pass,
   3. an identical deterministic merge on every rank (so no broadcast), local slice by
      split_length_idx (utils/public_function.py:720-746),
-and the three collectives of utils/stats/dist_stats.py:18-79 by a single all_reduce of a 5-vector.
+and the three collectives of utils/stats/dist_stats.py:18-79 by a single all_gather of seven doubles per rank
+(shifted moments; combined exactly, and lazily -- the host read can be left outside the step).
 """
 from __future__ import annotations
 
@@ -55,17 +56,28 @@ def exchange_unique_samples(onv: Tensor, psi: Tensor, counts: Optional[Tensor] =
         n_max = max(n_list)
         ragged = min(n_list) != n_max
 
-        # the columns travel as they are: no packing pass (a coalesced launch of the all-gathers measured slower)
+        # ONE collective: the columns of a rank travel as one byte buffer [keys | psi | counts] (a concatenation of
+        # flat views: one small copy kernel here, one per column on the far side) instead of one all-gather per column
         cols = [onv.contiguous(), torch.view_as_real(psi).contiguous() if psi.dtype.is_complex else psi.contiguous()]
         if counts is not None:  # counts travel only when the caller has them (unit counts otherwise)
             cols.append(counts.to(torch.int64).contiguous())
+        row_bytes = [math.prod(t.shape[1:]) * t.element_size() for t in cols]
         if ragged:
             cols = [torch.cat([t, t.new_zeros((n_max - n_r,) + tuple(t.shape[1:]))]) if n_r < n_max else t for t in cols]
-        outs = [torch.empty((world * n_max,) + tuple(t.shape[1:]), dtype=t.dtype, device=dev) for t in cols]
-        for o, t in zip(outs, cols):
-            dist.all_gather_into_tensor(o, t)
-        if ragged:  # drop the padding rows
-            outs = [torch.cat([o[r * n_max : r * n_max + n_list[r]] for r in range(world)]) for o in outs]
+        send = torch.cat([t.view(torch.uint8).reshape(-1) for t in cols])
+        per_rank = send.numel()
+        recv = torch.empty(world * per_rank, dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(recv, send)
+        recv = recv.view(world, per_rank)
+        outs, o = [], 0
+        for t, rb in zip(cols, row_bytes):
+            blk = recv[:, o : o + n_max * rb].reshape(world, n_max, rb)
+            if ragged:  # drop the padding rows
+                flat = torch.cat([blk[r, : n_list[r]] for r in range(world)])
+            else:
+                flat = blk.reshape(world * n_max, rb).contiguous()
+            outs.append(flat.view(t.dtype).reshape((flat.size(0),) + tuple(t.shape[1:])))
+            o += n_max * rb
         all_onv = outs[0]
         all_psi = torch.view_as_complex(outs[1]) if psi.dtype.is_complex else outs[1]
         all_cnt = outs[2] if counts is not None else torch.ones(all_onv.size(0), dtype=torch.int64, device=dev)
@@ -122,7 +134,42 @@ def _local_moments(e: Tensor, weight: Tensor, amplitude: bool) -> Tensor:
     return torch.cat([mom, tail])
 
 
-def _combine_moments(eloc: Tensor, weight: Tensor, amplitude: bool, counts: Optional[int]) -> dict:
+class PendingStatistics:
+    """Energy statistics whose per-rank moments are on the device (after the collective): `result()` does the one
+    host read and the exact combination.  Lets a caller keep the D2H read outside a timed / graph-captured step."""
+
+    def __init__(self, allv: Tensor, world: int, amplitude: bool, cplx: bool, counts: Optional[int]):
+        self._allv, self._world, self._amplitude, self._cplx, self._counts = allv, world, amplitude, cplx, counts
+        self._out: Optional[dict] = None
+
+    def result(self) -> dict:
+        if self._out is not None:
+            return self._out
+        world, cplx = self._world, self._cplx
+        rows = self._allv.tolist()  # the only host synchronisation of the statistics; plain floats from here on
+        z = sum(r[0] for r in rows)
+        # amplitudes: p_i = |psi_i|^2 / Z * W with Z over all ranks (sample.py:772 convention)
+        scale = (world / z if z > 0 else 0.0) if self._amplitude else 1.0
+        parts = []
+        for w, s_re, s_im, s_sq, c_re, c_im, _n in rows:
+            if w == 0.0:
+                continue
+            dm_re, dm_im = s_re / w, s_im / w
+            parts.append((w * scale, c_re + dm_re, c_im + dm_im, (s_sq - w * (dm_re * dm_re + dm_im * dm_im)) * scale))
+        mean_re = math.fsum(w * mr for w, mr, _, _ in parts) / world
+        mean_im = math.fsum(w * mi for w, _, mi, _ in parts) / world
+        var = math.fsum(m2 + w * ((mr - mean_re) ** 2 + (mi - mean_im) ** 2) for w, mr, mi, m2 in parts) / world
+        n = int(sum(r[6] for r in rows)) if self._counts is None else self._counts
+        sd = max(var, 0.0) ** 0.5
+        mean = complex(mean_re, mean_im) if cplx else mean_re
+        self._out = {"mean": mean, "var": var, "sd": sd, "se": sd / n ** 0.5 if n else 0.0, "n": n}
+        return self._out
+
+    def __getitem__(self, k):
+        return self.result()[k]
+
+
+def _combine_moments(eloc: Tensor, weight: Tensor, amplitude: bool, counts: Optional[int], lazy: bool = False):
     rank, world = _world()
     cplx = eloc.is_complex()
     e = eloc.to(torch.complex128) if cplx else eloc.to(torch.float64)
@@ -133,36 +180,22 @@ def _combine_moments(eloc: Tensor, weight: Tensor, amplitude: bool, counts: Opti
         allv = allv.view(world, 7)
     else:
         allv = vec.view(1, 7)
-    rows = allv.tolist()  # the only host synchronisation of the statistics; plain floats from here on
-    z = sum(r[0] for r in rows)
-    # amplitudes: p_i = |psi_i|^2 / Z * W with Z over all ranks (sample.py:772 convention)
-    scale = (world / z if z > 0 else 0.0) if amplitude else 1.0
-    parts = []
-    for w, s_re, s_im, s_sq, c_re, c_im, _n in rows:
-        if w == 0.0:
-            continue
-        dm_re, dm_im = s_re / w, s_im / w
-        parts.append((w * scale, c_re + dm_re, c_im + dm_im, (s_sq - w * (dm_re * dm_re + dm_im * dm_im)) * scale))
-    mean_re = math.fsum(w * mr for w, mr, _, _ in parts) / world
-    mean_im = math.fsum(w * mi for w, _, mi, _ in parts) / world
-    var = math.fsum(m2 + w * ((mr - mean_re) ** 2 + (mi - mean_im) ** 2) for w, mr, mi, m2 in parts) / world
-    n = int(sum(r[6] for r in rows)) if counts is None else counts
-    sd = max(var, 0.0) ** 0.5
-    mean = complex(mean_re, mean_im) if cplx else mean_re
-    return {"mean": mean, "var": var, "sd": sd, "se": sd / n ** 0.5 if n else 0.0, "n": n}
+    pending = PendingStatistics(allv, world, amplitude, cplx, counts)
+    return pending if lazy else pending.result()
 
 
-def energy_statistics(eloc: Tensor, prob: Tensor, counts: Optional[int] = None) -> dict:
+def energy_statistics(eloc: Tensor, prob: Tensor, counts: Optional[int] = None, lazy: bool = False):
     """mean / var / sd / se of the local energy -- the quantities of utils/stats/dist_stats.py:18-79
     (mean = sum_ranks sum_i p_i E_i / W and var = sum_ranks sum_i p_i |mean - E_i|^2 / W with
     p = prob * W, sample.py:772 + comm.py:65-67) from ONE kernel and ONE collective: an all_gather of
     the per-rank shifted moments, combined on the host with the exact identity
-    sum p|E - m|^2 = sum p|E - mu|^2 + (sum p)|mu - m|^2."""
-    return _combine_moments(eloc, prob, False, counts)
+    sum p|E - m|^2 = sum p|E - mu|^2 + (sum p)|mu - m|^2.  lazy=True returns a PendingStatistics: the collective is
+    issued, the host read happens at .result()."""
+    return _combine_moments(eloc, prob, False, counts, lazy)
 
 
-def energy_statistics_amplitudes(eloc: Tensor, psi0: Tensor, counts: Optional[int] = None) -> dict:
+def energy_statistics_amplitudes(eloc: Tensor, psi0: Tensor, counts: Optional[int] = None, lazy: bool = False):
     """Same statistics with p_i = |psi0_i|^2 / Z * W, Z = sum over ALL ranks' rows of |psi0|^2 -- the
     sample-space probabilities when the ranks' slices partition the unique set (build_shared_lut).
     Z comes out of the same all_gather, so the probabilities are never materialised."""
-    return _combine_moments(eloc, psi0, True, counts)
+    return _combine_moments(eloc, psi0, True, counts, lazy)
