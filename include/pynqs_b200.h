@@ -167,6 +167,15 @@ int64_t pynqs_moments_scratch_bytes(void);
 int pynqs_weighted_moments(const void *eloc, int eloc_complex, const void *weight, int weight_kind, int64_t n, void *scratch,
                            double *out, void *stream);
 
+/* Test / experiment knobs of the one-pass local energy (process-wide, not thread-safe; production code never
+ * calls this).  name: "scan_threads" (0 = automatic, 64, 128, 256), "search_factor" (bucket-size factor above which
+ * a group is searched instead of walked, default 64), "full_keys" (1: one-word ONVs take the full-key route of
+ * multi-word ONVs), "block_enable" (0: per-sample kernel only), "block_min_samples" (calls with fewer samples use the
+ * per-sample kernel only, default 4096), "block_min_group" (samples sharing a beta string needed for a tile of the
+ * block kernel, default 8).  name == NULL restores every default.  The scratch size of pynqs_eloc_scratch_bytes
+ * depends on the knobs: set them before sizing the scratch. */
+int pynqs_set_tuning(const char *name, int64_t value);
+
 /* number of kernel launches issued by this library in this process (bench.py's gpu_launches). */
 int64_t pynqs_launch_count(void);
 

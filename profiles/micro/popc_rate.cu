@@ -29,15 +29,23 @@ __global__ void __launch_bounds__(256) rate_kernel(const unsigned *__restrict__ 
       } else if (MODE == 1) {
         const unsigned t = d & (d - 1u);
         if (t != 0u && (t & (t - 1u)) == 0u) cnt++;
-      } else {
+      } else if (MODE == 2) {
         if (__popc(d) == 2) {
           q[qa & 2047] = (unsigned)(it * kUnroll + u);
           qa += 256;
         }
+      } else if (MODE == 3) {
+        const unsigned t = d & (d - 1u);
+        if (t != 0u && (t & (t - 1u)) == 0u) {
+          q[qa & 2047] = (unsigned)(it * kUnroll + u);
+          qa += 256;
+        }
+      } else {  // bit mask of the hits of this iteration, no store
+        if (__popc(d) == 2) cnt |= 1u << u;
       }
     }
   }
-  out[blockIdx.x * blockDim.x + threadIdx.x] = cnt + qa + q[threadIdx.x];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = (MODE == 2 || MODE == 3) ? cnt + qa + q[threadIdx.x] : cnt + qa;
 }
 
 int main() {
@@ -62,14 +70,17 @@ int main() {
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0);
   cudaEventCreate(&e1);
-  const char *names[3] = {"A xor+popc+setp+@p add", "B popc-free two-bit test", "C xor+popc+setp+@p sts+@p add"};
-  for (int mode = 0; mode < 3; ++mode) {
+  const char *names[5] = {"A xor+popc+setp+@p add", "B popc-free two-bit test", "C xor+popc+setp+@p sts+@p add", "D popc-free + @p sts + @p add",
+                          "E xor+popc+setp+@p or-mask"};
+  for (int mode = 0; mode < 5; ++mode) {
     float best = 1e30f;
     for (int rep = 0; rep < 5; ++rep) {
       cudaEventRecord(e0);
       if (mode == 0) rate_kernel<0><<<blocks, 256>>>(dk, dout, nkeys);
       else if (mode == 1) rate_kernel<1><<<blocks, 256>>>(dk, dout, nkeys);
-      else rate_kernel<2><<<blocks, 256>>>(dk, dout, nkeys);
+      else if (mode == 2) rate_kernel<2><<<blocks, 256>>>(dk, dout, nkeys);
+      else if (mode == 3) rate_kernel<3><<<blocks, 256>>>(dk, dout, nkeys);
+      else rate_kernel<4><<<blocks, 256>>>(dk, dout, nkeys);
       cudaEventRecord(e1);
       cudaEventSynchronize(e1);
       float ms;

@@ -17,7 +17,7 @@ SYMBOLS = [
     "pynqs_group_bytes", "pynqs_group_build", "pynqs_eloc_scratch_bytes", "pynqs_eloc_sample_space",
     "pynqs_reduce_scratch_bytes", "pynqs_reduce_count", "pynqs_reduce_emit", "pynqs_reduce_eloc",
     "pynqs_merge_rank_sample", "pynqs_sort_bytes", "pynqs_sort_table", "pynqs_moments_scratch_bytes", "pynqs_weighted_moments",
-    "pynqs_launch_count",
+    "pynqs_set_tuning", "pynqs_launch_count",
 ]
 
 OK, EVALUE, EOVERFLOW, ECUDA, EWORKSPACE = 0, 1, 2, 3, 4
@@ -67,6 +67,11 @@ def check(rc: int) -> None:
     if rc == EOVERFLOW:
         raise OverflowError(msg)
     raise RuntimeError(msg)
+
+
+def set_tuning(name=None, value: int = 0) -> None:
+    """Test / experiment knobs of the one-pass local energy (include/pynqs_b200.h); set_tuning() restores the defaults."""
+    check(load().pynqs_set_tuning(name.encode() if name is not None else None, ctypes.c_int64(int(value))))
 
 
 def launch_count() -> int:

@@ -6,7 +6,9 @@
 #include <cstdio>
 
 #include "../../include/pynqs_b200.h"
-#include "common.cuh"
+#include <cstring>
+
+#include "eloc.cuh"
 
 namespace pynqs {
 
@@ -261,6 +263,33 @@ int pynqs_group_bytes(int64_t N, int L, int64_t *bytes) {
 int pynqs_group_build(const uint8_t *key, int64_t N, int L, void *group_ws, int64_t group_bytes, void *stream) {
   if (int rc = check_L(L)) return rc;
   return launch_group_build(reinterpret_cast<const u64 *>(key), N, L, group_ws, group_bytes, (cudaStream_t)stream);
+}
+
+int pynqs_set_tuning(const char *name, int64_t value) {
+  ElocTuning &t = eloc_tuning();
+  struct {
+    const char *name;
+    int *field;
+    long long lo, hi;
+  } knobs[] = {{"scan_threads", &t.scan_threads, 0, 256},        {"search_factor", &t.search_factor, 1, 4096},
+               {"full_keys", &t.full_keys, 0, 1},                {"block_min_samples", &t.block_min_samples, 1, 1LL << 30},
+               {"block_min_group", &t.block_min_group, 4, 32},   {"block_enable", &t.block_enable, 0, 1}};
+  if (name == nullptr) {
+    t = ElocTuning();  // back to the production values
+    return 0;
+  }
+  for (auto &k : knobs) {
+    if (strcmp(name, k.name) == 0) {
+      if (value < k.lo || value > k.hi) {
+        set_error("tuning knob %s: value %lld outside [%lld, %lld]", name, (long long)value, k.lo, k.hi);
+        return PYNQS_EVALUE;
+      }
+      *k.field = (int)value;
+      return 0;
+    }
+  }
+  set_error("unknown tuning knob '%s'", name);
+  return PYNQS_EVALUE;
 }
 
 int pynqs_eloc_scratch_bytes(int64_t n, int sorb, int noA, int noB, int psi_complex, int64_t *bytes) {

@@ -28,9 +28,7 @@
 // table -- the same set binary_search_BigInteger would find.  Tables with duplicate keys, and
 // samples whose hits overflow the queues, take the reference's route instead (enumerate every
 // excitation, classic binary search); no floating point atomics anywhere.
-#include <cstdlib>
-
-#include "gindex.cuh"
+#include "eloc.cuh"
 #include "lut.cuh"
 #include "rederive.cuh"
 #include "tables.cuh"
@@ -40,8 +38,6 @@ namespace pynqs {
 constexpr int kMaxScanWarps = 8;   // scan kernel: 2, 4 or 8 warps per CTA, by the number of groups of a sample
 constexpr int kQueue = 512;        // hits per warp before the sample falls back to the full route
 constexpr int kEvalThreads = 128;  // eval kernel: 4 samples per CTA
-constexpr u32 kOverflow = 0x80000000u;
-constexpr u32 kNoSelf = 0xffffffffu;
 
 struct Cplx {
   double re, im;
@@ -112,10 +108,10 @@ __device__ __forceinline__ Onv<L> msk_apply(const Onv<L> &x, u64 m) {
   return y;
 }
 
-// per (sample, slice, warp) run of hits in the global buffer
-struct HitRun {
-  u32 off, cnt;  // cnt & kOverflow: a queue or the buffer overflowed -> the sample takes the full route
-};
+ElocTuning &eloc_tuning() {
+  static ElocTuning t;
+  return t;
+}
 
 // hit = position in the grouped copy | grouping << 31
 __device__ __forceinline__ void push_hits(u32 *queue, u32 &qn, bool hit, u32 value) {
@@ -268,10 +264,6 @@ __host__ __device__ inline ScanSmem scan_smem(const ExcGeom &g, int warps) {
 // orbital (bit of the ONV word) of position f of a folded beta string (inverse of fold_beta)
 __device__ __forceinline__ u32 unfold_beta(u32 f) { return (f & 1u) ? 32u + f : f + 1u; }
 
-// hit word: position in the grouped copy | kHitA (alpha-grouped copy) | kHitOwn (found in the scan of one of
-// the sample's own strings, HALF route only -- the eval kernel checks the class of the key accordingly)
-constexpr u32 kHitA = 0x80000000u, kHitOwn = 0x40000000u, kHitPos = 0x3fffffffu;
-
 // Small groups are cut into 32-key chunks and all chunks of a sample are processed as one flat, evenly
 // divided list (a warp would otherwise idle on its small groups while another one walks a large group);
 // larger groups are walked (or searched) by one warp each.
@@ -279,8 +271,9 @@ constexpr u32 kHitA = 0x80000000u, kHitOwn = 0x40000000u, kHitPos = 0x3fffffffu;
 // by hash collision, which the eval kernel detects on the full key.
 template <int L, bool HALF, int THREADS>
 __global__ void __launch_bounds__(THREADS)
-eloc_scan_kernel(const u64 *__restrict__ bra, long long n, GroupView gv, HitRun *__restrict__ runs, u32 *__restrict__ hits,
-                 u32 *__restrict__ self_pos, u32 *cursor, u32 hit_cap, int splits, ExcGeom g, ScanSmem sm) {
+eloc_scan_kernel(const u64 *__restrict__ bra, long long n, GroupView gv, HitRun *__restrict__ runs, u32 *__restrict__ run_cnt,
+                 int run_stride, u32 *__restrict__ hits, u32 *__restrict__ self_pos, ElocCounters *ctr, u32 hit_cap, int splits,
+                 const u32 *__restrict__ ids, ExcGeom g, ScanSmem sm) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int sB = g.noB * g.nvB, nG = sB + 2;
   OrbLists &lists = *reinterpret_cast<OrbLists *>(smem_raw);
@@ -301,14 +294,19 @@ eloc_scan_kernel(const u64 *__restrict__ bra, long long n, GroupView gv, HitRun 
   __shared__ u32 wtot[80];  // work per (round of THREADS groups, warp); nG <= 2306 -> at most 37 x 2 entries
   __shared__ SearchGeom s_sg[3];
 
-  const long long s = splits == 1 ? (long long)blockIdx.x : (long long)(blockIdx.x / (unsigned)splits);
-  const int split = splits == 1 ? 0 : (int)(blockIdx.x - (unsigned)s * (unsigned)splits);
-  if (s >= n) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  HitRun *my_run = runs + (s * splits + split) * kScanWarps + warp;
   // duplicate keys in the table: the eval kernel takes the reference's route for every sample.  The flag is
   // loaded here and looked at only when the run record is written, so no CTA starts by waiting for it.
   const u32 table_has_dup = __ldg(&gv.hdr->has_dup);
+  // work items: (sample, slice of its groups) pairs -- every sample of the call, or (ids != nullptr) the samples
+  // the grouping pass of the block route left to this kernel: the last n_single entries of ids[0, n)
+  const long long items = ids != nullptr ? (long long)ctr->n_single : n * splits;
+  for (long long item = blockIdx.x; item < items; item += gridDim.x) {
+  const long long it_s = splits == 1 ? item : item / splits;
+  const int split = splits == 1 ? 0 : (int)(item - it_s * splits);
+  const long long s = ids != nullptr ? (long long)ids[n - 1 - it_s] : it_s;
+  HitRun *my_run = runs + s * run_stride + split * kScanWarps + warp;
+  if (threadIdx.x == 0 && split == 0) run_cnt[s] = (u32)(splits * kScanWarps);
   const Onv<L> x = load_onv<L>(bra + s * L);
   // HALF: the beta singles are picked straight out of the folded beta string (n-th set bit); the orbital lists
   // are only built when a group has to be searched
@@ -614,7 +612,7 @@ eloc_scan_kernel(const u64 *__restrict__ bra, long long n, GroupView gv, HitRun 
   u32 off = 0;
   bool over = qn > (u32)kQueue || table_has_dup != 0u;
   if (lane == 0 && !over && qn) {
-    off = atomicAdd(cursor, qn);
+    off = atomicAdd(&ctr->hit_cursor, qn);
     if (off > hit_cap || qn > hit_cap - off) over = true;  // buffer exhausted
   }
   off = __shfl_sync(0xffffffffu, off, 0);
@@ -625,6 +623,8 @@ eloc_scan_kernel(const u64 *__restrict__ bra, long long n, GroupView gv, HitRun 
   }
   if (!over)
     for (u32 e = lane; e < qn; e += 32) hits[off + e] = queue[e];
+  __syncthreads();  // the next item reuses the shared arrays
+  }
 }
 
 // ---- evaluation ---------------------------------------------------------------------------------------------
@@ -632,16 +632,16 @@ template <int L, bool CPLX, bool HALF>
 __global__ void __launch_bounds__(kEvalThreads, 12)
 eloc_eval_kernel(const u64 *__restrict__ bra, long long n, const double *__restrict__ h1e, const double *__restrict__ h2e,
                  const u64 *__restrict__ key, const double *__restrict__ psi, long long N, GroupView gv,
-                 const HitRun *__restrict__ runs, const u32 *__restrict__ hits, const u32 *__restrict__ self_pos,
-                 const double *__restrict__ hii, double *__restrict__ eloc, double *__restrict__ psi0_out, int splits, int scan_warps,
-                 ExcGeom g) {
+                 const HitRun *__restrict__ runs, const u32 *__restrict__ run_cnt, int run_stride, const u32 *__restrict__ hits,
+                 const u32 *__restrict__ self_pos, const double *__restrict__ hii, double *__restrict__ eloc,
+                 double *__restrict__ psi0_out, ExcGeom g) {
   __shared__ OrbLists s_lists[kEvalThreads / 32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long s = (long long)blockIdx.x * (kEvalThreads / 32) + warp;
   if (s >= n) return;
   const Onv<L> x = load_onv<L>(bra + s * L);
-  const int nruns = splits * scan_warps;
-  const HitRun *my_runs = runs + s * nruns;
+  const int nruns = (int)run_cnt[s];
+  const HitRun *my_runs = runs + s * run_stride;
   bool redo = false;
   for (int w = lane; w < nruns; w += 32) redo |= (my_runs[w].cnt & kOverflow) != 0;
   redo = __any_sync(0xffffffffu, redo);
@@ -753,10 +753,8 @@ eloc_eval_kernel(const u64 *__restrict__ bra, long long n, const double *__restr
 // ---- host side --------------------------------------------------------------------------------------------
 // splits: CTAs per sample -- more than one only when there are too few samples to fill the GPU
 static int scan_threads(int n_groups) {
-  if (const char *e = getenv("PYNQS_SCAN_THREADS")) {  // experiments only
-    const int t = atoi(e);
-    if (t == 64 || t == 128 || t == 256) return t;
-  }
+  const int t = eloc_tuning().scan_threads;
+  if (t == 64 || t == 128 || t == 256) return t;
   return n_groups <= 192 ? 128 : 256;
 }
 
@@ -768,36 +766,73 @@ static int scan_splits(long long n, int n_groups, int warps) {
   return (int)(want < 1 ? 1 : want);
 }
 
+// block route (eloc_block.cu)
+long long block_scratch_bytes(long long n);
+int block_run_stride();
+int launch_eloc_block(const u64 *bra, long long n, const GroupView &gv, char *block_ws, ElocCounters *ctr, HitRun *runs, u32 *run_cnt,
+                      int run_stride, u32 *hits, u32 *self_pos, u32 hit_cap, const ExcGeom &g, const u32 **slots_out, cudaStream_t st);
+
 struct ElocScratch {
-  long long hii, self_pos, runs, cursor, hits, total;
+  long long hii, self_pos, run_cnt, runs, counters, block_ws, hits, total;
   long long hit_cap, batch;
-  int splits;  // same for every batch of the call (sized for the first, largest one)
-  int warps;   // warps per scan CTA
+  int splits;      // same for every batch of the call (sized for the first, largest one)
+  int warps;       // warps per scan CTA
+  int run_stride;  // HitRun records per sample
+  bool block;      // samples grouped by beta string first (eloc_block.cu); the per-sample kernel takes the rest
 };
 
-static ElocScratch eloc_scratch_layout(long long n, const ExcGeom &g) {
+// the block route needs one-word ONVs (decided again at launch: it also needs N < 2^30 and the folded route)
+static bool block_route_wanted(long long n, const ExcGeom &g) {
+  const ElocTuning &t = eloc_tuning();
+  return t.block_enable && !t.full_keys && g.L == 1 && n >= t.block_min_samples && g.noB * g.nvB + 2 <= 258;
+}
+
+static ElocScratch eloc_scratch_layout(long long n, const ExcGeom &g, bool block) {
   ElocScratch l;
-  // hits per sample the global buffer can take before samples fall back to the full route, and a
-  // batch size that keeps the buffer at about 2 GiB
-  long long per_sample = (long long)g.nsd / 4;
-  per_sample = per_sample < 256 ? 256 : (per_sample > 4096 ? 4096 : per_sample);
-  l.batch = (1LL << 29) / per_sample;
-  l.batch = l.batch < 1024 ? 1024 : (l.batch > (1LL << 18) ? (1LL << 18) : l.batch);
-  const long long nb = n < l.batch ? n : l.batch;
+  l.block = block;
   l.warps = scan_threads(g.noB * g.nvB + 2) / 32;
-  l.splits = scan_splits(nb, g.noB * g.nvB + 2, l.warps);
-  l.hii = 0;
-  l.self_pos = (l.hii + 8 * n + 15) / 16 * 16;
-  l.runs = (l.self_pos + 4 * nb + 15) / 16 * 16;
-  l.cursor = l.runs + (long long)sizeof(HitRun) * nb * l.splits * kMaxScanWarps;
-  l.hits = l.cursor + 256;
-  l.hit_cap = nb * per_sample + 65536;
+  if (block) {
+    // every sample of the call in one go (the samples of a beta string must stay together); hits per sample the
+    // buffer can take before samples fall back to the full route: 256 on average, at most 8 GiB in all
+    l.batch = n < (1LL << 24) ? n : (1LL << 24);
+    l.splits = 1;
+    l.run_stride = block_run_stride() > l.warps ? block_run_stride() : l.warps;
+    l.hit_cap = l.batch * 256 + 65536;
+  } else {
+    // hits per sample the global buffer can take before samples fall back to the full route, and a
+    // batch size that keeps the buffer at about 2 GiB
+    long long per_sample = (long long)g.nsd / 4;
+    per_sample = per_sample < 256 ? 256 : (per_sample > 4096 ? 4096 : per_sample);
+    l.batch = (1LL << 29) / per_sample;
+    l.batch = l.batch < 1024 ? 1024 : (l.batch > (1LL << 18) ? (1LL << 18) : l.batch);
+    const long long nb0 = n < l.batch ? n : l.batch;
+    l.splits = scan_splits(nb0, g.noB * g.nvB + 2, l.warps);
+    l.run_stride = l.splits * l.warps;
+    l.hit_cap = nb0 * per_sample + 65536;
+  }
+  const long long nb = n < l.batch ? n : l.batch;
   if (l.hit_cap > 0x7fffffffLL) l.hit_cap = 0x7fffffffLL;
+  auto up = [](long long v) { return (v + 255) & ~255LL; };
+  l.hii = 0;
+  l.self_pos = up(l.hii + 8 * n);
+  l.run_cnt = up(l.self_pos + 4 * nb);
+  l.runs = up(l.run_cnt + 4 * nb);
+  l.counters = up(l.runs + (long long)sizeof(HitRun) * nb * l.run_stride);
+  l.block_ws = l.counters + 256;
+  l.hits = up(l.block_ws + (block ? block_scratch_bytes(nb) : 0));
   l.total = l.hits + 4 * l.hit_cap + 256;
   return l;
 }
 
-long long eloc_scratch_bytes(long long n, const ExcGeom &g) { return eloc_scratch_layout(n, g).total; }
+// the caller's scratch serves either route (the route also depends on the table, which this function does not see)
+long long eloc_scratch_bytes(long long n, const ExcGeom &g) {
+  long long t = eloc_scratch_layout(n, g, false).total;
+  if (block_route_wanted(n, g)) {
+    const long long tb = eloc_scratch_layout(n, g, true).total;
+    if (tb > t) t = tb;
+  }
+  return t;
+}
 
 int launch_diag_f64(const u64 *bra, const double *h1e, const double *h2e, double *out, long long n, long long stride, int L,
                     int sorb, int nele, cudaStream_t st);
@@ -808,14 +843,13 @@ static int launch_eloc_LC(const u64 *bra, long long n, const double *h1e, const 
                           const ExcGeom &g, cudaStream_t st) {
   double *hii = reinterpret_cast<double *>(scratch + lay.hii);
   u32 *self_pos = reinterpret_cast<u32 *>(scratch + lay.self_pos);
+  u32 *run_cnt = reinterpret_cast<u32 *>(scratch + lay.run_cnt);
   HitRun *runs = reinterpret_cast<HitRun *>(scratch + lay.runs);
-  u32 *cursor = reinterpret_cast<u32 *>(scratch + lay.cursor);
+  ElocCounters *ctr = reinterpret_cast<ElocCounters *>(scratch + lay.counters);
   u32 *hits = reinterpret_cast<u32 *>(scratch + lay.hits);
   ScanSmem sm = scan_smem(g, lay.warps);
-  if (const char *e = getenv("PYNQS_SEARCH_FACTOR")) {  // parity tests: force the search route on small tables
-    const int f = atoi(e);
-    if (f >= 1 && f <= 4096) sm.search_factor = (u32)f;
-  }
+  const int f = eloc_tuning().search_factor;  // parity tests: force the search route on small tables
+  if (f >= 1 && f <= 4096) sm.search_factor = (u32)f;
   const size_t smem = sm.total;
   if (smem > 227 * 1024) {
     set_error("eloc: %zu bytes of shared memory per CTA needed for sorb = %d, noA = %d, noB = %d (limit 227 KB)", smem, g.sorb, g.noA, g.noB);
@@ -828,15 +862,26 @@ static int launch_eloc_LC(const u64 *bra, long long n, const double *h1e, const 
   for (long long b0 = 0; b0 < n; b0 += lay.batch) {
     const long long nb = n - b0 < lay.batch ? n - b0 : lay.batch;
     const int splits = lay.splits;
-    if (cudaMemsetAsync(cursor, 0, 4, st) != cudaSuccess) return check_launch("eloc cursor memset");
+    if (cudaMemsetAsync(ctr, 0, sizeof(ElocCounters), st) != cudaSuccess) return check_launch("eloc counters memset");
     if (cudaMemsetAsync(self_pos, 0xff, 4 * (size_t)nb, st) != cudaSuccess) return check_launch("eloc self memset");
-    scan<<<(unsigned)(nb * splits), lay.warps * 32, smem, st>>>(bra + b0 * L, nb, gv, runs, hits, self_pos, cursor,
-                                                                              (u32)lay.hit_cap, splits, g, sm);
+    const u32 *ids = nullptr;
+    unsigned grid = (unsigned)(nb * splits);
+    if (HALF && lay.block) {
+      // samples that share a beta string with enough others: tiles of the block kernel; the rest: per-sample kernel,
+      // which finds its work list (and its length) in device memory -- a fixed grid of persistent CTAs
+      if (int rc = launch_eloc_block(bra + b0 * L, nb, gv, scratch + lay.block_ws, ctr, runs, run_cnt, lay.run_stride, hits, self_pos,
+                                     (u32)lay.hit_cap, g, &ids, st))
+        return rc;
+      const long long cap = 148LL * 12;
+      grid = (unsigned)(nb < cap ? nb : cap);
+    }
+    scan<<<grid, lay.warps * 32, smem, st>>>(bra + b0 * L, nb, gv, runs, run_cnt, lay.run_stride, hits, self_pos, ctr, (u32)lay.hit_cap,
+                                             splits, ids, g, sm);
     count_launch();
     if (int rc = check_launch("eloc_scan_kernel")) return rc;
     const unsigned eb = (unsigned)((nb + kEvalThreads / 32 - 1) / (kEvalThreads / 32));
-    eloc_eval_kernel<L, CPLX, HALF><<<eb, kEvalThreads, 0, st>>>(bra + b0 * L, nb, h1e, h2e, key, psi, N, gv, runs, hits, self_pos,
-                                                            hii + b0, eloc + b0 * w, psi0 + b0 * w, splits, lay.warps, g);
+    eloc_eval_kernel<L, CPLX, HALF><<<eb, kEvalThreads, 0, st>>>(bra + b0 * L, nb, h1e, h2e, key, psi, N, gv, runs, run_cnt, lay.run_stride,
+                                                                 hits, self_pos, hii + b0, eloc + b0 * w, psi0 + b0 * w, g);
     count_launch();
     if (int rc = check_launch("eloc_eval_kernel")) return rc;
   }
@@ -847,7 +892,10 @@ int launch_eloc(const u64 *bra, long long n, const double *h1e, const double *h2
                 long long N, const void *group_ws, void *scratch, long long scratch_bytes, double *eloc, double *psi0,
                 const ExcGeom &g, cudaStream_t st) {
   if (n == 0) return 0;
-  const ElocScratch lay = eloc_scratch_layout(n, g);
+  // folded 32-bit strings: one-word ONVs, two flag bits in the hit word.  The tuning knob full_keys forces the
+  // full-key route (the one multi-word ONVs take) -- used by the parity tests to cover both.
+  const bool half = g.L == 1 && N < (1LL << 30) && !eloc_tuning().full_keys;
+  const ElocScratch lay = eloc_scratch_layout(n, g, half && block_route_wanted(n, g));
   if (scratch_bytes < lay.total) {
     set_error("eloc scratch too small: %lld < %lld bytes", scratch_bytes, lay.total);
     return 4;
@@ -859,10 +907,7 @@ int launch_eloc(const u64 *bra, long long n, const double *h1e, const double *h2
   case LL:                                                                                                                   \
     return cplx ? launch_eloc_LC<LL, true, false>(bra, n, h1e, h2e, key, psi, N, gv, sc, lay, eloc, psi0, g, st)             \
                 : launch_eloc_LC<LL, false, false>(bra, n, h1e, h2e, key, psi, N, gv, sc, lay, eloc, psi0, g, st);
-  // folded 32-bit strings: one-word ONVs, two flag bits in the hit word.  PYNQS_FULL_KEYS=1 forces the
-  // full-key route (the one multi-word ONVs take) -- used by the parity tests to cover both.
-  const char *full = getenv("PYNQS_FULL_KEYS");
-  if (g.L == 1 && N < (1LL << 30) && !(full && full[0] == '1')) {
+  if (half) {
     return cplx ? launch_eloc_LC<1, true, true>(bra, n, h1e, h2e, key, psi, N, gv, sc, lay, eloc, psi0, g, st)
                 : launch_eloc_LC<1, false, true>(bra, n, h1e, h2e, key, psi, N, gv, sc, lay, eloc, psi0, g, st);
   }

@@ -197,14 +197,28 @@ def test_empty_and_tiny_inputs():
 
 
 # ---- E_loc ------------------------------------------------------------------------------------------
-@pytest.fixture(params=["folded", "full_keys"])
-def scan_route(request, monkeypatch):
-    """One-word ONVs are scanned through folded 32-bit strings; PYNQS_FULL_KEYS=1 forces the full-key
-    route that multi-word ONVs (and tables of 2^30 keys or more) take.  Both must give the same numbers."""
+@pytest.fixture(autouse=True)
+def _default_tuning():
+    from pynqs_b200 import _lib
+
+    _lib.set_tuning()
+    yield
+    _lib.set_tuning()
+
+
+@pytest.fixture(params=["folded", "full_keys", "block"])
+def scan_route(request):
+    """One-word ONVs are scanned through folded 32-bit strings; the knob full_keys forces the full-key
+    route that multi-word ONVs (and tables of 2^30 keys or more) take; "block" sends every call, however small, through
+    the grouping pass and the block kernel (samples sharing a beta string walk their groups together), with tiles from
+    4 samples on.  All must give the same numbers."""
+    from pynqs_b200 import _lib
+
     if request.param == "full_keys":
-        monkeypatch.setenv("PYNQS_FULL_KEYS", "1")
-    else:
-        monkeypatch.delenv("PYNQS_FULL_KEYS", raising=False)
+        _lib.set_tuning("full_keys", 1)
+    elif request.param == "block":
+        _lib.set_tuning("block_min_samples", 1)
+        _lib.set_tuning("block_min_group", 4)
     return request.param
 
 
@@ -254,12 +268,14 @@ def test_eloc_sample_missing_from_table_gives_nan_like_reference():
 
 
 @pytest.mark.parametrize("search_factor", ["64", "8"])
-def test_eloc_dense_table_full_space(scan_route, search_factor, monkeypatch):
+def test_eloc_dense_table_full_space(scan_route, search_factor):
     """Full 24-spin-orbital space (6a6b, 853 776 keys): EVERY connected determinant is in the table
     (1819 hits per sample) and the groups are large enough (924 keys) for the alpha-beta groups to be
     searched instead of walked when the threshold is lowered (factor 8) -- the result must equal the oracle and
     the three-call path either way."""
-    monkeypatch.setenv("PYNQS_SEARCH_FACTOR", search_factor)
+    from pynqs_b200 import _lib
+
+    _lib.set_tuning("search_factor", int(search_factor))
     sorb, noA, noB, nele = 24, 6, 6, 12
     import itertools
 
@@ -312,13 +328,15 @@ def test_eloc_hit_queue_overflow_takes_the_full_route(scan_route):
 
 
 @pytest.mark.parametrize("alpha_only", [True, False])
-def test_eloc_one_huge_group_is_searched(alpha_only, scan_route, monkeypatch):
+def test_eloc_one_huge_group_is_searched(alpha_only, scan_route):
     """36 spin orbitals, 9 electrons of ONE spin: the whole table (all 48 620 strings) is a single group,
     35x larger than the 1378 determinants connected to a sample -> with the search threshold lowered to 16x the
     own-string bucket is searched (binary search inside the bucket) instead of walked."""
     import itertools
 
-    monkeypatch.setenv("PYNQS_SEARCH_FACTOR", "16")
+    from pynqs_b200 import _lib
+
+    _lib.set_tuning("search_factor", 16)
 
     sorb = 36
     noA, noB = (9, 0) if alpha_only else (0, 9)
