@@ -144,6 +144,23 @@ int pynqs_reduce_emit(const uint8_t *bra, const void *h1e, const void *h2e, cons
 int pynqs_reduce_eloc(const void *psi, int psi_complex, const double *hij, const int64_t *idx, const int64_t *offsets, int64_t n,
                       int64_t M, void *eloc, void *psi0, void *stream);
 
+/* Stochastic / semi-stochastic branch of the REDUCE method (vmc/energy/eloc.py:257-283, eps_sample > 0; what every
+ * shipped input selects, main.py:149-159): per sample, eps_sample draws from p(m) ~ |H_m| over the rows with |H_m| < eps
+ * (all rows when eps == 0); a drawn row's element becomes (count / eps_sample) * H_m / p(m) = sign(H_m) * S * count /
+ * eps_sample with S the sample's sum of sub-eps magnitudes; rows with |H_m| >= eps (eps > 0) are kept exactly.  Same
+ * count / emit protocol and outputs as pynqs_reduce_count / _emit; per sample the kept rows come first (ascending m), then
+ * the drawn rows (ascending m).  No [n, M] array and no [n, eps_sample] array is materialised.
+ * Draws: Philox4x32-10 keyed by `seed` (reproducible; not torch.multinomial's stream), or -- draws != NULL -- the caller's
+ * row indices int64[n, eps_sample] (what torch.multinomial returned), which makes the result a deterministic function of
+ * the inputs.  eps_sample <= 8192.  scratch: pynqs_reduce_sample_scratch_bytes(n) bytes, the same buffer for both calls. */
+int64_t pynqs_reduce_sample_scratch_bytes(int64_t n);
+int pynqs_reduce_sample_count(const uint8_t *bra, const void *h1e, const void *h2e, int64_t n, int sorb, int nele, int noA, int noB,
+                              double eps, int eps_sample, uint64_t seed, const int64_t *draws, int dtype, void *scratch,
+                              int64_t scratch_bytes, int64_t *offsets, void *stream);
+int pynqs_reduce_sample_emit(const uint8_t *bra, const void *h1e, const void *h2e, int64_t n, int sorb, int nele, int noA, int noB,
+                             double eps, int eps_sample, uint64_t seed, const int64_t *draws, int dtype, void *scratch,
+                             int64_t scratch_bytes, const int64_t *offsets, uint8_t *x, void *hij, int64_t *idx, void *stream);
+
 /* ---- unique-sample table: sort (utils/public_function.py:626-689, 754-788) ----------------------
  * Stable ascending sort of N keys (uint64[N, L] little-endian multi-word integers, the order of the
  * reference's torch_sort_onv) together with their psi values (psi_bytes = 8 or 16 per row; psi may

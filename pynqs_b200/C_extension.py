@@ -36,8 +36,9 @@ def _need_cuda(*tensors: Tensor) -> torch.device:
         if not isinstance(t, Tensor):
             raise TypeError(f"expected torch.Tensor, got {type(t)}")
         if not t.is_cuda:
-            raise RuntimeError(
-                "pynqs_b200 ops are CUDA-only (no CPU fallback): move the tensors to a B200 device"
+            raise NotImplementedError(
+                "pynqs_b200 operators are CUDA-only (no CPU fallback, by design): move the tensors to a B200 device, or keep "
+                "the reference's CPU build of libs.C_extension for host-side callers (CI matrices, gloo runs) -- INTEGRATION.md section 4"
             )
         if dev is None:
             dev = t.device
@@ -128,7 +129,7 @@ def onv_to_tensor(bra: Tensor, sorb: int) -> Tensor:
     _contig(bra, "bra")
     if bra.dim() not in (1, 2):
         raise ValueError("bra must be 1-D or 2-D")
-    L = _onv_words(bra, "bra")
+    L = _check_width(bra, sorb, "bra")  # the kernel strides by ceil(sorb / 64) words
     bra2 = bra.view(-1, 8 * L)
     dtype = torch.get_default_dtype()
     if dtype not in (torch.float32, torch.float64):
@@ -193,17 +194,32 @@ class PreparedIntegrals:
 _prep_cache: dict = {}
 # preparing costs one pass over ~(sorb/2)^4 elements: only worth it when the call writes more than that
 _PREP_MIN_OUTPUT_RATIO = 4
+# the prepared copy is O((sorb/2)^4) elements (1.07 GB in FP64 at 192 spin orbitals): get_comb_hij_fused only builds
+# one on its own below this size (above it the packed arrays are read directly -- identical results), and at most
+# _PREP_CACHE_ENTRIES of them are kept alive (least recently used first out)
+PREPARED_AUTO_MAX_BYTES = 2 << 30
+_PREP_CACHE_ENTRIES = 4
+
+
+def prepared_nbytes(sorb: int, dtype: torch.dtype) -> int:
+    nbytes = _lib.ctypes.c_int64()
+    code = _lib.F64 if dtype == torch.float64 else _lib.F32
+    _lib.check(_lib.load().pynqs_prepared_bytes(int(sorb), code, _lib.ctypes.byref(nbytes)))
+    return int(nbytes.value)
 
 
 def _cached_prep(h2e: Tensor, sorb: int) -> PreparedIntegrals:
     """Per-tensor-object cache: valid while the same h2e tensor object is alive and unmodified."""
     k = id(h2e)
-    ent = _prep_cache.get(k)
+    ent = _prep_cache.pop(k, None)
     if ent is not None:
         ref, version, ptr, prep = ent
         if ref() is h2e and version == h2e._version and ptr == h2e.data_ptr() and prep.sorb == sorb:
+            _prep_cache[k] = ent  # most recently used last
             return prep
     prep = PreparedIntegrals(h2e, sorb)
+    while len(_prep_cache) >= _PREP_CACHE_ENTRIES:
+        _prep_cache.pop(next(iter(_prep_cache)))
     _prep_cache[k] = (weakref.ref(h2e, lambda _r, k=k: _prep_cache.pop(k, None)), h2e._version, h2e.data_ptr(), prep)
     return prep
 
@@ -229,6 +245,8 @@ def get_comb_hij_fused(bra: Tensor, h1e: Tensor, h2e: Tensor, sorb: int, nele: i
         if prepared is None:
             na = sorb // 2
             big = n * M >= _PREP_MIN_OUTPUT_RATIO * (na**4 + sorb**3) or id(h2e) in _prep_cache
+            if big and id(h2e) not in _prep_cache and prepared_nbytes(sorb, h2e.dtype) > PREPARED_AUTO_MAX_BYTES:
+                big = False  # too large to build unasked: pass a PreparedIntegrals explicitly to use the table-driven kernel
             prepared = _cached_prep(h2e, sorb) if big else False
         prep_ptr = prepared.workspace.data_ptr() if prepared else None
         if prepared and (prepared.sorb != sorb or prepared.dtype != h2e.dtype):
@@ -283,6 +301,59 @@ def get_comb_hij_reduced(bra: Tensor, h1e: Tensor, h2e: Tensor, sorb: int, nele:
         idx = torch.empty(K, dtype=torch.int64, device=dev)
         _lib.check(lib.pynqs_reduce_emit(*common, vp(offsets.data_ptr()), vp(x.data_ptr()), vp(hij.data_ptr()), vp(idx.data_ptr()),
                                          _stream(dev)))
+    return x, hij, idx, offsets
+
+
+def get_comb_hij_sampled(bra: Tensor, h1e: Tensor, h2e: Tensor, sorb: int, nele: int, noA: int, noB: int, eps: float, eps_sample: int,
+                         *, seed: int | None = None, draws: Tensor | None = None) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    """Additive op for the stochastic / semi-stochastic REDUCE method (vmc/energy/eloc.py:257-283, eps_sample > 0):
+    per sample, eps_sample draws from p(m) ~ |H_m| over the rows with |H_m| < eps (all rows if eps == 0); the element of a
+    drawn row becomes (count / eps_sample) * H_m / p(m); rows with |H_m| >= eps (eps > 0) are kept exactly.
+    Returns (x uint8 [K, 8L], hij [K], gt_eps_idx int64 [K], offsets int64 [n + 1]) like get_comb_hij_reduced; per sample the
+    kept rows (ascending) come first, then the drawn ones (ascending).  Nothing of size [n, M] or [n, eps_sample] is stored.
+    seed: Philox key (default: drawn from torch's CPU generator, so torch.manual_seed makes runs reproducible);
+    draws: int64 [n, eps_sample] row indices to use instead of the generator (what torch.multinomial returned)."""
+    dev = _need_cuda(bra, h1e, h2e)
+    for t, nm in ((bra, "bra"), (h1e, "h1e"), (h2e, "h2e")):
+        _contig(t, nm)
+    if bra.dim() == 1:
+        bra = bra.view(1, -1)
+    L = _check_width(bra, sorb, "bra")
+    code = _fdtype(h1e, h2e)
+    _check_integrals(h1e, h2e, sorb)
+    M = get_Num_SinglesDoubles(sorb, noA, noB) + 1
+    if not (eps >= 0.0) or int(eps_sample) < 1:
+        raise ValueError("eps must be >= 0 and eps_sample >= 1")
+    n = bra.size(0)
+    offsets = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+    if n == 0:
+        return (torch.empty((0, 8 * L), dtype=torch.uint8, device=dev), torch.empty(0, dtype=h1e.dtype, device=dev),
+                torch.empty(0, dtype=torch.int64, device=dev), offsets)
+    draws_ptr = None
+    if draws is not None:
+        _need_cuda(draws)
+        draws = draws.to(torch.int64).contiguous()
+        if draws.shape != (n, int(eps_sample)):
+            raise ValueError(f"draws must be [n, eps_sample] = [{n}, {eps_sample}]")
+        if int(draws.min()) < 0 or int(draws.max()) >= M:
+            raise ValueError("draws: row index outside [0, M)")
+        draws_ptr = draws.data_ptr()
+    if seed is None:
+        seed = int(torch.randint(0, 2**62, (1,)).item())
+    lib = _lib.load()
+    nbytes = int(lib.pynqs_reduce_sample_scratch_bytes(i64(n)))
+    scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    common = (vp(bra.data_ptr()), vp(h1e.data_ptr()), vp(h2e.data_ptr()), i64(n), int(sorb), int(nele), int(noA), int(noB),
+              _lib.ctypes.c_double(float(eps)), int(eps_sample), _lib.ctypes.c_uint64(int(seed) & (2**64 - 1)), vp(draws_ptr), code,
+              vp(scratch.data_ptr()), i64(nbytes))
+    with torch.cuda.device(dev):
+        _lib.check(lib.pynqs_reduce_sample_count(*common, vp(offsets.data_ptr()), _stream(dev)))
+        K = int(offsets[n].item())
+        x = torch.empty((K, 8 * L), dtype=torch.uint8, device=dev)
+        hij = torch.empty(K, dtype=h1e.dtype, device=dev)
+        idx = torch.empty(K, dtype=torch.int64, device=dev)
+        _lib.check(lib.pynqs_reduce_sample_emit(*common, vp(offsets.data_ptr()), vp(x.data_ptr()), vp(hij.data_ptr()), vp(idx.data_ptr()),
+                                                _stream(dev)))
     return x, hij, idx, offsets
 
 
@@ -352,6 +423,7 @@ class HashIndex:
         _contig(bra_key, "bra_key")
         self.L = _onv_words(bra_key, "bra_key")
         self.N = bra_key.size(0)
+        self.key_ptr = bra_key.data_ptr()
         nbytes = _lib.ctypes.c_int64()
         _lib.check(_lib.load().pynqs_hash_bytes(i64(self.N), self.L, _lib.ctypes.byref(nbytes)))
         self.workspace = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
@@ -368,6 +440,11 @@ class HashIndex:
 
 
 _hash_cache: dict = {}
+
+
+def hash_worthwhile(n_queries: int, n_keys: int) -> bool:
+    """The hash index costs ~200 bytes per key to build: only for query batches that amortise it."""
+    return n_queries >= _HASH_MIN_QUERIES and 8 * n_queries >= n_keys and n_keys < (1 << 32)
 
 
 def _cached_hash(bra_key: Tensor) -> HashIndex:
@@ -393,6 +470,7 @@ class GroupIndex:
         _contig(bra_key, "bra_key")
         self.L = _onv_words(bra_key, "bra_key")
         self.N = bra_key.size(0)
+        self.key_ptr = bra_key.data_ptr()
         nbytes = _lib.ctypes.c_int64()
         _lib.check(_lib.load().pynqs_group_bytes(i64(self.N), self.L, _lib.ctypes.byref(nbytes)))
         self.workspace = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
@@ -424,10 +502,13 @@ def _cached_group(bra_key: Tensor) -> GroupIndex:
     return gidx
 
 
-def wavefunction_lut(bra_key: Tensor, onv: Tensor, sorb: int, little_endian: bool = True, *, hash_index: HashIndex | None = None) -> Tuple[Tensor, Tensor]:
+def wavefunction_lut(bra_key: Tensor, onv: Tensor, sorb: int, little_endian: bool = True, *,
+                     hash_index: "HashIndex | None | bool" = None) -> Tuple[Tensor, Tensor]:
     """Index of every onv row in the sorted key table (C_extension.pyi:305-357): (idx int64 [n]
     with -1 for absent rows, mask bool [n]).  The ONV width comes from the tensors, not from
-    `sorb` (DetLUT passes a prefix length, utils/det_helper/determinant_lut.py:285-291)."""
+    `sorb` (DetLUT passes a prefix length, utils/det_helper/determinant_lut.py:285-291).
+    hash_index: a HashIndex of bra_key; None = build / reuse one when the query batch is large enough to pay for it
+    (~200 bytes per key); False = always the classic binary search."""
     if not little_endian:
         raise NotImplementedError("little_endian=False is broken in the reference (cpu_tensor.cpp:613) and never used")
     dev = _need_cuda(bra_key, onv)
@@ -442,10 +523,12 @@ def wavefunction_lut(bra_key: Tensor, onv: Tensor, sorb: int, little_endian: boo
     if n == 0:
         return idx, mask
     lib = _lib.load()
-    if hash_index is None and n >= _HASH_MIN_QUERIES and 8 * n >= N and N < (1 << 32):
+    if hash_index is None and hash_worthwhile(n, N):
         hash_index = _cached_hash(bra_key)
+    if hash_index is not None and hash_index is not False and (hash_index.N != N or hash_index.L != L or hash_index.key_ptr != bra_key.data_ptr()):
+        raise ValueError("hash_index was built for another key table")
     with torch.cuda.device(dev):
-        if hash_index is not None:
+        if hash_index:
             _lib.check(
                 lib.pynqs_lut_hashed(
                     vp(bra_key.data_ptr()), i64(N), vp(onv.data_ptr()), i64(n), L, vp(hash_index.workspace.data_ptr()),
@@ -469,6 +552,8 @@ def eloc_sample_space(
     dev = _need_cuda(bra, h1e, h2e, bra_key, wf_value)
     for t, nm in ((bra, "bra"), (h1e, "h1e"), (h2e, "h2e"), (bra_key, "bra_key"), (wf_value, "wf_value")):
         _contig(t, nm)
+    if bra.dim() != 2 or bra_key.dim() != 2 or wf_value.dim() != 1:
+        raise ValueError("bra and bra_key must be 2-D [rows, 8L], wf_value 1-D")
     L = _check_width(bra, sorb, "bra")
     if _onv_words(bra_key, "bra_key") != L:
         raise ValueError("bra and bra_key widths differ")
@@ -485,7 +570,7 @@ def eloc_sample_space(
         return eloc, psi0
     if group_index is None:
         group_index = _cached_group(bra_key)
-    if group_index.N != N or group_index.L != L:
+    if group_index.N != N or group_index.L != L or group_index.key_ptr != bra_key.data_ptr():
         raise ValueError("group_index was built for another key table")
     lib = _lib.load()
     nbytes = _lib.ctypes.c_int64()

@@ -16,6 +16,7 @@ SYMBOLS = [
     "pynqs_lut", "pynqs_hash_bytes", "pynqs_hash_build", "pynqs_lut_hashed",
     "pynqs_group_bytes", "pynqs_group_build", "pynqs_eloc_scratch_bytes", "pynqs_eloc_sample_space",
     "pynqs_reduce_scratch_bytes", "pynqs_reduce_count", "pynqs_reduce_emit", "pynqs_reduce_eloc",
+    "pynqs_reduce_sample_scratch_bytes", "pynqs_reduce_sample_count", "pynqs_reduce_sample_emit",
     "pynqs_merge_rank_sample", "pynqs_sort_bytes", "pynqs_sort_table", "pynqs_moments_scratch_bytes", "pynqs_weighted_moments",
     "pynqs_set_tuning", "pynqs_launch_count",
 ]
@@ -45,6 +46,7 @@ def load() -> ctypes.CDLL:
     lib.pynqs_last_error.restype = ctypes.c_char_p
     lib.pynqs_launch_count.restype = ctypes.c_int64
     lib.pynqs_reduce_scratch_bytes.restype = ctypes.c_int64
+    lib.pynqs_reduce_sample_scratch_bytes.restype = ctypes.c_int64
     lib.pynqs_sort_bytes.restype = ctypes.c_int64
     lib.pynqs_moments_scratch_bytes.restype = ctypes.c_int64
     if lib.pynqs_abi_version() != 1:

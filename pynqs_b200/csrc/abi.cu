@@ -63,6 +63,10 @@ int launch_reduce(const u64 *, const T *, const T *, const void *, long long, co
                   long long *, u64 *, T *, long long *, cudaStream_t);
 int launch_reduce_eloc(const double *, int, const double *, const long long *, const long long *, long long, long long, double *,
                        double *, cudaStream_t);
+long long reduce_sample_scratch_bytes(long long);
+template <typename T>
+int launch_reduce_sample(const u64 *, const T *, const T *, long long, const ExcGeom &, double, int, unsigned long long, const long long *, int,
+                         void *, long long, long long *, u64 *, T *, long long *, cudaStream_t);
 int launch_merge_counts(const long long *, const long long *, long long, long long, long long *, cudaStream_t);
 int launch_onv_to_tensor(const u64 *, void *, int, long long, int, cudaStream_t);
 int launch_tensor_to_onv(const unsigned char *, unsigned char *, long long, int, cudaStream_t);
@@ -357,6 +361,49 @@ int pynqs_reduce_emit(const uint8_t *bra, const void *h1e, const void *h2e, cons
                       uint8_t *x, void *hij, int64_t *idx, void *stream) {
   return reduce_common(bra, h1e, h2e, prep_ws, n, sorb, nele, noA, noB, eps, dtype, 1, scratch, scratch_bytes,
                        const_cast<int64_t *>(offsets), x, hij, idx, stream);
+}
+
+int64_t pynqs_reduce_sample_scratch_bytes(int64_t n) { return reduce_sample_scratch_bytes(n); }
+
+static int reduce_sample_common(const uint8_t *bra, const void *h1e, const void *h2e, int64_t n, int sorb, int nele, int noA, int noB,
+                                double eps, int eps_sample, uint64_t seed, const int64_t *draws, int dtype, int emit, void *scratch,
+                                int64_t scratch_bytes, int64_t *offsets, uint8_t *x, void *hij, int64_t *idx, void *stream) {
+  if (int rc = check_geometry(sorb, nele, noA, noB)) return rc;
+  long long nsd;
+  if (int rc = num_sd_checked(sorb, noA, noB, &nsd)) return rc;
+  if (dtype != PYNQS_F32 && dtype != PYNQS_F64) {
+    set_error("reduce_sample: dtype %d is neither float32 nor float64", dtype);
+    return PYNQS_EVALUE;
+  }
+  if (n < 0 || !(eps >= 0.0) || eps_sample < 1) {
+    set_error("reduce_sample: bad n = %lld, eps = %g or eps_sample = %d", (long long)n, eps, eps_sample);
+    return PYNQS_EVALUE;
+  }
+  const ExcGeom g = make_geom(sorb, nele, noA, noB);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == PYNQS_F64)
+    return launch_reduce_sample<double>(reinterpret_cast<const u64 *>(bra), (const double *)h1e, (const double *)h2e, n, g, eps, eps_sample,
+                                        seed, reinterpret_cast<const long long *>(draws), emit, scratch, scratch_bytes,
+                                        reinterpret_cast<long long *>(offsets), reinterpret_cast<u64 *>(x), (double *)hij,
+                                        reinterpret_cast<long long *>(idx), st);
+  return launch_reduce_sample<float>(reinterpret_cast<const u64 *>(bra), (const float *)h1e, (const float *)h2e, n, g, eps, eps_sample, seed,
+                                     reinterpret_cast<const long long *>(draws), emit, scratch, scratch_bytes,
+                                     reinterpret_cast<long long *>(offsets), reinterpret_cast<u64 *>(x), (float *)hij,
+                                     reinterpret_cast<long long *>(idx), st);
+}
+
+int pynqs_reduce_sample_count(const uint8_t *bra, const void *h1e, const void *h2e, int64_t n, int sorb, int nele, int noA, int noB,
+                              double eps, int eps_sample, uint64_t seed, const int64_t *draws, int dtype, void *scratch,
+                              int64_t scratch_bytes, int64_t *offsets, void *stream) {
+  return reduce_sample_common(bra, h1e, h2e, n, sorb, nele, noA, noB, eps, eps_sample, seed, draws, dtype, 0, scratch, scratch_bytes, offsets,
+                              nullptr, nullptr, nullptr, stream);
+}
+
+int pynqs_reduce_sample_emit(const uint8_t *bra, const void *h1e, const void *h2e, int64_t n, int sorb, int nele, int noA, int noB,
+                             double eps, int eps_sample, uint64_t seed, const int64_t *draws, int dtype, void *scratch,
+                             int64_t scratch_bytes, const int64_t *offsets, uint8_t *x, void *hij, int64_t *idx, void *stream) {
+  return reduce_sample_common(bra, h1e, h2e, n, sorb, nele, noA, noB, eps, eps_sample, seed, draws, dtype, 1, scratch, scratch_bytes,
+                              const_cast<int64_t *>(offsets), x, hij, idx, stream);
 }
 
 int pynqs_reduce_eloc(const void *psi, int psi_complex, const double *hij, const int64_t *idx, const int64_t *offsets, int64_t n,

@@ -533,6 +533,17 @@ int launch_diag_f64(const u64 *bra, const double *h1e, const double *h2e, double
   return 1;
 }
 
+// the same for either element type (reduce_sample.cu)
+template <int L, typename T>
+int launch_diag_plain(const u64 *bra, const T *h1e, const T *h2e, T *out, long long n, long long stride, int sorb, int nele, cudaStream_t st) {
+  return launch_diag_LT<L, T>(bra, h1e, h2e, out, n, stride, sorb, nele, st);
+}
+#define PYNQS_DIAG_INST(LL, TT) \
+  template int launch_diag_plain<LL, TT>(const u64 *, const TT *, const TT *, TT *, long long, long long, int, int, cudaStream_t);
+PYNQS_DIAG_INST(1, double) PYNQS_DIAG_INST(2, double) PYNQS_DIAG_INST(3, double)
+PYNQS_DIAG_INST(1, float) PYNQS_DIAG_INST(2, float) PYNQS_DIAG_INST(3, float)
+#undef PYNQS_DIAG_INST
+
 int launch_states(const u64 *comb, double *states, long long rows, int sorb, cudaStream_t st) {
   const int L = (sorb - 1) / 64 + 1;
   const long long total = rows * sorb;
@@ -760,9 +771,18 @@ reduce_eloc_kernel(const double *__restrict__ psi, const double *__restrict__ hi
   if (s >= n) return;
   const long long b = offsets[s], e = offsets[s + 1];
   double p0r = 0.0, p0i = 0.0;
-  if (b < e && idx[b] == s * M) {
-    p0r = CPLX ? psi[2 * b] : psi[b];
-    p0i = CPLX ? psi[2 * b + 1] : 0.0;
+  // row 0 of the sample (flat index s * M): first of the kept rows, or -- stochastic branch with a sub-eps diagonal --
+  // first of the drawn rows; absent: psi0 = 0 like the reference
+  long long k0 = -1;
+  for (long long k = b + lane; k < e && k0 < 0; k += 32)
+    if (idx[k] == s * M) k0 = k;
+  {
+    const u32 found = __ballot_sync(0xffffffffu, k0 >= 0);
+    if (found) {
+      k0 = __shfl_sync(0xffffffffu, k0, __ffs(found) - 1);
+      p0r = CPLX ? psi[2 * k0] : psi[k0];
+      p0i = CPLX ? psi[2 * k0 + 1] : 0.0;
+    }
   }
   double ar = 0.0, ai = 0.0;
   for (long long k = b + lane; k < e; k += 32) {

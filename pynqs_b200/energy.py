@@ -49,9 +49,12 @@ def local_energy_three_call(x: Tensor, h1e: Tensor, h2e: Tensor, WF_LUT: Wavefun
 
 
 def local_energy_reduced(x: Tensor, h1e: Tensor, h2e: Tensor, psi_of, sorb: int, nele: int, noa: int, nob: int,
-                         dtype=torch.double, eps: float = 1.0e-12, batch: int = 65536) -> Tuple[Tensor, Tensor, Tensor]:
-    """ElocMethod.REDUCE, deterministic branch (eps > 0, eps_sample = 0; eloc.py:257-297): only the connected
-    determinants with |<x|H|x'>| >= eps enter E_loc.  `psi_of(x_kept uint8 [K, 8L]) -> Tensor [K]` supplies the
+                         dtype=torch.double, eps: float = 1.0e-12, batch: int = 65536, eps_sample: int = 0, seed=None,
+                         draws=None) -> Tuple[Tensor, Tensor, Tensor]:
+    """ElocMethod.REDUCE (eloc.py:204-323).  eps_sample = 0: only the connected determinants with |<x|H|x'>| >= eps enter
+    E_loc.  eps_sample > 0 (the setting of the shipped inputs, main.py:149-159): the sub-eps rows are importance-sampled,
+    eps_sample draws per sample from p ~ |H|, and enter with (count / eps_sample) * H / p (eloc.py:257-283); `seed` / `draws`
+    as in get_comb_hij_sampled (`draws` [n, eps_sample] covers all of x, it is sliced per batch).  `psi_of(x_kept uint8 [K, 8L]) -> Tensor [K]` supplies the
     amplitudes (the reference's Func(ansatz, x, WF_LUT, use_unique)); a WavefunctionLUT may be passed instead,
     absent determinants then count as 0.  Returns (eloc, sloc, psi_x) like _reduce_psi."""
     M = ops.get_Num_SinglesDoubles(sorb, noa, nob) + 1
@@ -66,7 +69,12 @@ def local_energy_reduced(x: Tensor, h1e: Tensor, h2e: Tensor, psi_of, sorb: int,
 
     elocs, psis = [], []
     for b in range(0, x.size(0), batch):
-        xk, hij, idx, offsets = ops.get_comb_hij_reduced(x[b : b + batch], h1e, h2e, sorb, nele, noa, nob, eps)
+        if eps_sample > 0:
+            xk, hij, idx, offsets = ops.get_comb_hij_sampled(
+                x[b : b + batch], h1e, h2e, sorb, nele, noa, nob, eps, eps_sample,
+                seed=None if seed is None else int(seed) + b, draws=None if draws is None else draws[b : b + batch])
+        else:
+            xk, hij, idx, offsets = ops.get_comb_hij_reduced(x[b : b + batch], h1e, h2e, sorb, nele, noa, nob, eps)
         psi = psi_of(xk)
         psi = psi.to(torch.complex128 if psi.is_complex() else torch.float64)
         e, p0 = ops.reduce_eloc(psi, hij, idx, offsets, M)

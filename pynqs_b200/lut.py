@@ -139,9 +139,12 @@ class WavefunctionLUT:
     def lookup(self, onv: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
         """(positions of onv rows found in the table, positions not found, table values of the found rows)
         -- public_function.py:817-838."""
-        from .C_extension import wavefunction_lut
+        from .C_extension import hash_worthwhile, wavefunction_lut
 
-        idx_array, mask = wavefunction_lut(self._bra_key, onv, self.sorb, hash_index=self.hash_index)
+        # the hash index (~200 bytes per key) is only built for query batches that pay for it; small ones take the
+        # classic binary search like the reference
+        use_hash = self._bra_key.is_cuda and (self._hash is not None or hash_worthwhile(onv.size(0), self._bra_key.size(0)))
+        idx_array, mask = wavefunction_lut(self._bra_key, onv, self.sorb, hash_index=self.hash_index if use_hash else False)
         baseline = torch.arange(onv.size(0), device=onv.device, dtype=torch.int64)
         onv_idx = baseline[mask]
         onv_not_idx = baseline[torch.logical_not(mask)]

@@ -241,8 +241,68 @@ def main_simple():
     save("simple_fe2s2", **out)
 
 
+def main_reduce_sample():
+    """Stochastic / semi-stochastic REDUCE goldens (vmc.energy.eloc._reduce_psi of the reference, eps_sample > 0) on the Fe2S2
+    integrals, toy ansatz.  torch.multinomial is wrapped so that the draws it returned are stored with the golden: the
+    reference result is a deterministic function of (inputs, draws), which is what the GPU test reproduces."""
+    torch.set_num_threads(os.cpu_count())
+    ref = load_ref(1)
+    libs = types.ModuleType("libs")
+    libs.__path__ = []
+    sys.modules["libs"] = libs
+    sys.modules["libs.C_extension"] = ref
+    libs.C_extension = ref
+    sys.path.insert(0, REFERENCE)
+    from vmc.energy.eloc import _reduce_psi  # reference code
+
+    d = torch.load(os.path.join(REFERENCE, "example/Fe2S2/fe2s2-OO.pth"), weights_only=False)
+    h1e, h2e = d["h1e"], d["h2e"]
+    ci = d["ci_space"].numpy()
+    sorb, noA, noB, nele = int(d["sorb"]), int(d["noa"]), int(d["nob"]), int(d["nele"])
+    first, n = 2000, 24
+    x = t(ci[first : first + n].copy())
+    out = dict(first=first, n=n)
+    real_multinomial = torch.multinomial
+    for mode, eps, ns in (("semi", 1.0e-2, 1000), ("pure", 0.0, 500)):
+        torch.manual_seed(2024)
+        kept = {}
+
+        def recording(prob, num, replacement=False, **kw):
+            r = real_multinomial(prob, num, replacement=replacement, **kw)
+            kept["draws"] = r.clone()
+            return r
+
+        for tag, cplx in (("real", False), ("complex", True)):
+            dtype = torch.complex128 if cplx else torch.double
+
+            def ansatz(states):
+                return toy_amplitude(states, sorb, cplx)
+
+            def batcher(x, func):
+                return func(ref.onv_to_tensor(x, sorb)).to(dtype)
+
+            if "draws" in kept:  # same draws for the complex run
+                fixed = kept["draws"]
+                torch.multinomial = lambda prob, num, replacement=False, **kw: fixed.clone()
+            else:
+                torch.multinomial = recording
+            try:
+                eloc, _, psi_x, _ = _reduce_psi(x, h1e, h2e, ansatz, batcher, sorb, nele, noA, noB, dtype=dtype, WF_LUT=None,
+                                                use_unique=True, eps=eps, eps_sample=ns)
+            finally:
+                torch.multinomial = real_multinomial
+            out[f"{mode}_eloc_{tag}"] = eloc.numpy()
+            out[f"{mode}_psi_x_{tag}"] = psi_x.numpy()
+        out[f"{mode}_draws"] = kept["draws"].numpy().astype(np.int16)
+        out[f"{mode}_eps"] = eps
+        out[f"{mode}_eps_sample"] = ns
+    save("reduce_sample_fe2s2", **out)
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "reduce":
+    if len(sys.argv) > 1 and sys.argv[1] == "reduce_sample":
+        main_reduce_sample()
+    elif len(sys.argv) > 1 and sys.argv[1] == "reduce":
         main_reduce()
     elif len(sys.argv) > 1 and sys.argv[1] == "simple":
         main_simple()
@@ -250,3 +310,4 @@ if __name__ == "__main__":
         main()
         main_reduce()
         main_simple()
+        main_reduce_sample()
