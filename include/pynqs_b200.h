@@ -171,6 +171,25 @@ int64_t pynqs_sort_bytes(int64_t N);
 int pynqs_sort_table(const uint8_t *key, const void *psi, int64_t N, int L, int sorb, int psi_bytes, uint8_t *key_out,
                      void *psi_out, int64_t *perm_out, void *ws, int64_t ws_bytes, void *stream);
 
+/* ---- index glue of the lookup (additive) ------------------------------------------------------------------------
+ * WavefunctionLUT.lookup (utils/public_function.py:817-838) = wavefunction_lut + arange + two boolean-mask selections + a
+ * gather; pynqs_lookup_count / _emit produce its three results from (idx, mask) in two passes:
+ *   count: *n_hit (device, uint64) = number of set mask bytes;
+ *   emit : hit_pos int64[n_hit] (ascending positions with mask set), miss_pos int64[n - n_hit] (ascending positions
+ *          without), value[n_hit] = value_table[idx[hit_pos]] (value_bytes = 8 or 16 per element).
+ * Func (vmc/energy/flip.py:44-61) = torch.unique(rows, dim=0, return_inverse=True) of the LUT misses;
+ * pynqs_unique_count / _emit take the rows already sorted by pynqs_sort_table (sorted_key, perm):
+ *   count: *n_unique (device, uint64);   emit: unique uint8[n_unique, 8L] (ascending), inverse int64[n] with
+ *          unique[inverse[i]] == row i of the unsorted input.
+ * scratch: pynqs_compact_scratch_bytes(n) bytes, the same buffer for the count and the emit call. */
+int64_t pynqs_compact_scratch_bytes(int64_t n);
+int pynqs_lookup_count(const uint8_t *mask, int64_t n, void *scratch, int64_t scratch_bytes, uint64_t *n_hit, void *stream);
+int pynqs_lookup_emit(const uint8_t *mask, const int64_t *idx, int64_t n, const void *value_table, int value_bytes, void *scratch,
+                      int64_t *hit_pos, int64_t *miss_pos, void *value, void *stream);
+int pynqs_unique_count(const uint8_t *sorted_key, int64_t n, int L, void *scratch, int64_t scratch_bytes, uint64_t *n_unique, void *stream);
+int pynqs_unique_emit(const uint8_t *sorted_key, const int64_t *perm, int64_t n, int L, void *scratch, uint8_t *unique, int64_t *inverse,
+                      void *stream);
+
 /* merge_rank_sample (libs/C_extension.pyi:256-279; cpu_tensor.cpp:537-556): out int64[length] = 0, then
  * out[idx[i]] += counts[i] for i < n (int64 atomics; indices outside [0, length) are ignored). */
 int pynqs_merge_rank_sample(const int64_t *idx, const int64_t *counts, int64_t n, int64_t length, int64_t *out, void *stream);

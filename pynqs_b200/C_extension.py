@@ -587,6 +587,63 @@ def eloc_sample_space(
     return eloc, psi0
 
 
+def lookup_compact(idx_array: Tensor, mask: Tensor, wf_value: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
+    """(positions with mask set, positions without, wf_value[idx_array[mask]]) -- the index glue of
+    WavefunctionLUT.lookup (utils/public_function.py:825-838: arange, two boolean-mask selections, masked_select, gather)
+    in two passes of the library.  One host synchronisation (the number of hits), like the boolean indexing it replaces."""
+    dev = _need_cuda(idx_array, mask, wf_value)
+    n = idx_array.numel()
+    if mask.dtype != torch.bool or mask.numel() != n or idx_array.dtype != torch.int64:
+        raise ValueError("idx_array must be int64 and mask bool, of the same length")
+    if wf_value.dim() != 1 or wf_value.element_size() not in (8, 16):
+        raise ValueError("wf_value must be 1-D with 8- or 16-byte elements")
+    _contig(idx_array, "idx_array")
+    _contig(mask, "mask")
+    _contig(wf_value, "wf_value")
+    lib = _lib.load()
+    nbytes = int(lib.pynqs_compact_scratch_bytes(i64(n)))
+    scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    n_hit = torch.zeros(1, dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.pynqs_lookup_count(vp(mask.data_ptr()), i64(n), vp(scratch.data_ptr()), i64(nbytes), vp(n_hit.data_ptr()), _stream(dev)))
+        k = int(n_hit.item())
+        hit = torch.empty(k, dtype=torch.int64, device=dev)
+        miss = torch.empty(n - k, dtype=torch.int64, device=dev)
+        value = torch.empty(k, dtype=wf_value.dtype, device=dev)
+        _lib.check(lib.pynqs_lookup_emit(vp(mask.data_ptr()), vp(idx_array.data_ptr()), i64(n), vp(wf_value.data_ptr()),
+                                         int(wf_value.element_size()), vp(scratch.data_ptr()), vp(hit.data_ptr()), vp(miss.data_ptr()),
+                                         vp(value.data_ptr()), _stream(dev)))
+    return hit, miss, value
+
+
+def unique_onv(x: Tensor) -> Tuple[Tensor, Tensor]:
+    """(distinct rows of x, inverse) with unique[inverse] == x -- what Func (vmc/energy/flip.py:44-61) asks of
+    torch.unique(x, dim=0, return_inverse=True), on the library's radix sort instead of a comparison sort of rows.  The
+    distinct rows come out ascending as ONV integers (torch.unique orders them byte 0 first); callers that only use
+    unique[inverse] -- Func does -- see no difference."""
+    dev = _need_cuda(x)
+    _contig(x, "x")
+    if x.dim() != 2:
+        raise ValueError("x must be 2-D [rows, 8L]")
+    L = _onv_words(x, "x")
+    n = x.size(0)
+    inverse = torch.empty(n, dtype=torch.int64, device=dev)
+    if n == 0:
+        return x.clone(), inverse
+    key_sorted, _, perm = sort_table(x, None, 0, want_perm=True)
+    lib = _lib.load()
+    nbytes = int(lib.pynqs_compact_scratch_bytes(i64(n)))
+    scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    n_u = torch.zeros(1, dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.pynqs_unique_count(vp(key_sorted.data_ptr()), i64(n), L, vp(scratch.data_ptr()), i64(nbytes), vp(n_u.data_ptr()), _stream(dev)))
+        k = int(n_u.item())
+        uniq = torch.empty((k, 8 * L), dtype=torch.uint8, device=dev)
+        _lib.check(lib.pynqs_unique_emit(vp(key_sorted.data_ptr()), vp(perm.data_ptr()), i64(n), L, vp(scratch.data_ptr()), vp(uniq.data_ptr()),
+                                         vp(inverse.data_ptr()), _stream(dev)))
+    return uniq, inverse
+
+
 # ---- the steps either side of the kernels: table sort and energy moments ------------------------
 def sort_table(bra_key: Tensor, wf_value: Tensor | None = None, sorb: int = 0, want_perm: bool = True):
     """Stable ascending sort of ONV rows as little-endian multi-word integers -- the order of the

@@ -17,6 +17,7 @@ SYMBOLS = [
     "pynqs_group_bytes", "pynqs_group_build", "pynqs_eloc_scratch_bytes", "pynqs_eloc_sample_space",
     "pynqs_reduce_scratch_bytes", "pynqs_reduce_count", "pynqs_reduce_emit", "pynqs_reduce_eloc",
     "pynqs_reduce_sample_scratch_bytes", "pynqs_reduce_sample_count", "pynqs_reduce_sample_emit",
+    "pynqs_compact_scratch_bytes", "pynqs_lookup_count", "pynqs_lookup_emit", "pynqs_unique_count", "pynqs_unique_emit",
     "pynqs_merge_rank_sample", "pynqs_sort_bytes", "pynqs_sort_table", "pynqs_moments_scratch_bytes", "pynqs_weighted_moments",
     "pynqs_set_tuning", "pynqs_launch_count",
 ]
@@ -47,6 +48,7 @@ def load() -> ctypes.CDLL:
     lib.pynqs_launch_count.restype = ctypes.c_int64
     lib.pynqs_reduce_scratch_bytes.restype = ctypes.c_int64
     lib.pynqs_reduce_sample_scratch_bytes.restype = ctypes.c_int64
+    lib.pynqs_compact_scratch_bytes.restype = ctypes.c_int64
     lib.pynqs_sort_bytes.restype = ctypes.c_int64
     lib.pynqs_moments_scratch_bytes.restype = ctypes.c_int64
     if lib.pynqs_abi_version() != 1:

@@ -67,6 +67,12 @@ long long reduce_sample_scratch_bytes(long long);
 template <typename T>
 int launch_reduce_sample(const u64 *, const T *, const T *, long long, const ExcGeom &, double, int, unsigned long long, const long long *, int,
                          void *, long long, long long *, u64 *, T *, long long *, cudaStream_t);
+long long compact_scratch_bytes(long long);
+int launch_lookup_count(const unsigned char *, long long, void *, long long, unsigned long long *, cudaStream_t);
+int launch_lookup_emit(const unsigned char *, const long long *, long long, const void *, int, void *, long long *, long long *, void *,
+                       cudaStream_t);
+int launch_unique_count(const u64 *, long long, int, void *, long long, unsigned long long *, cudaStream_t);
+int launch_unique_emit(const u64 *, const long long *, long long, int, void *, u64 *, long long *, cudaStream_t);
 int launch_merge_counts(const long long *, const long long *, long long, long long, long long *, cudaStream_t);
 int launch_onv_to_tensor(const u64 *, void *, int, long long, int, cudaStream_t);
 int launch_tensor_to_onv(const unsigned char *, unsigned char *, long long, int, cudaStream_t);
@@ -414,6 +420,45 @@ int pynqs_reduce_eloc(const void *psi, int psi_complex, const double *hij, const
   }
   return launch_reduce_eloc((const double *)psi, psi_complex, hij, reinterpret_cast<const long long *>(idx),
                             reinterpret_cast<const long long *>(offsets), n, M, (double *)eloc, (double *)psi0, (cudaStream_t)stream);
+}
+
+int64_t pynqs_compact_scratch_bytes(int64_t n) { return compact_scratch_bytes(n); }
+
+int pynqs_lookup_count(const uint8_t *mask, int64_t n, void *scratch, int64_t scratch_bytes, uint64_t *n_hit, void *stream) {
+  if (n < 0) {
+    set_error("lookup_count: bad n = %lld", (long long)n);
+    return PYNQS_EVALUE;
+  }
+  return launch_lookup_count(mask, n, scratch, scratch_bytes, reinterpret_cast<unsigned long long *>(n_hit), (cudaStream_t)stream);
+}
+
+int pynqs_lookup_emit(const uint8_t *mask, const int64_t *idx, int64_t n, const void *value_table, int value_bytes, void *scratch,
+                      int64_t *hit_pos, int64_t *miss_pos, void *value, void *stream) {
+  if (n < 0 || (value_bytes != 8 && value_bytes != 16)) {
+    set_error("lookup_emit: bad n = %lld or value_bytes = %d", (long long)n, value_bytes);
+    return PYNQS_EVALUE;
+  }
+  return launch_lookup_emit(mask, reinterpret_cast<const long long *>(idx), n, value_table, value_bytes, scratch,
+                            reinterpret_cast<long long *>(hit_pos), reinterpret_cast<long long *>(miss_pos), value, (cudaStream_t)stream);
+}
+
+int pynqs_unique_count(const uint8_t *sorted_key, int64_t n, int L, void *scratch, int64_t scratch_bytes, uint64_t *n_unique, void *stream) {
+  if (n < 0 || L < 1 || L > PYNQS_MAX_SORB_LEN) {
+    set_error("unique_count: bad n = %lld or L = %d", (long long)n, L);
+    return PYNQS_EVALUE;
+  }
+  return launch_unique_count(reinterpret_cast<const u64 *>(sorted_key), n, L, scratch, scratch_bytes,
+                             reinterpret_cast<unsigned long long *>(n_unique), (cudaStream_t)stream);
+}
+
+int pynqs_unique_emit(const uint8_t *sorted_key, const int64_t *perm, int64_t n, int L, void *scratch, uint8_t *unique, int64_t *inverse,
+                      void *stream) {
+  if (n < 0 || L < 1 || L > PYNQS_MAX_SORB_LEN) {
+    set_error("unique_emit: bad n = %lld or L = %d", (long long)n, L);
+    return PYNQS_EVALUE;
+  }
+  return launch_unique_emit(reinterpret_cast<const u64 *>(sorted_key), reinterpret_cast<const long long *>(perm), n, L, scratch,
+                            reinterpret_cast<u64 *>(unique), reinterpret_cast<long long *>(inverse), (cudaStream_t)stream);
 }
 
 int64_t pynqs_sort_bytes(int64_t N) { return sort_workspace_bytes(N < 0 ? 0 : N); }

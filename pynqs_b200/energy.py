@@ -20,6 +20,28 @@ from . import C_extension as ops
 from .lut import WavefunctionLUT
 
 
+def Func(func, x: Tensor, WF_LUT: "WavefunctionLUT | None" = None, use_unique: bool = False) -> Tensor:
+    """psi of every row of x: table values where the LUT has the row, `func` (the ansatz) on the rest -- on the distinct
+    rows only when use_unique.  Mirror of vmc/energy/flip.py:29-63 on the library's lookup + compaction
+    (WavefunctionLUT.lookup) and its sort-based unique_onv instead of torch.unique(dim=0)."""
+    batch = x.size(0)
+    lut_idx = lut_not_idx = lut_value = None
+    if WF_LUT is not None:
+        lut_idx, lut_not_idx, lut_value = WF_LUT.lookup(x)
+        x = x[lut_not_idx]
+    if use_unique and x.size(0) > 0:
+        unique_x, inverse = ops.unique_onv(x.contiguous())
+        psi0 = torch.index_select(func(unique_x), 0, inverse)
+    else:
+        psi0 = func(x)
+    if WF_LUT is None:
+        return psi0
+    psi = torch.empty(batch, dtype=psi0.dtype, device=psi0.device)
+    psi[lut_idx] = lut_value.to(psi0.dtype)
+    psi[lut_not_idx] = psi0
+    return psi
+
+
 def local_energy_sample_space(x: Tensor, h1e: Tensor, h2e: Tensor, WF_LUT: WavefunctionLUT, sorb: int, nele: int,
                               noa: int, nob: int, dtype=torch.double) -> Tuple[Tensor, Tensor, Tensor]:
     """Returns (eloc, sloc, psi_x) like _only_sample_space (eloc.py:508); sloc is zero (no spin-raising)."""

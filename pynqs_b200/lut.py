@@ -145,6 +145,10 @@ class WavefunctionLUT:
         # classic binary search like the reference
         use_hash = self._bra_key.is_cuda and (self._hash is not None or hash_worthwhile(onv.size(0), self._bra_key.size(0)))
         idx_array, mask = wavefunction_lut(self._bra_key, onv, self.sorb, hash_index=self.hash_index if use_hash else False)
+        if self._wf_value.dim() == 1 and self._wf_value.element_size() in (8, 16):
+            from .C_extension import lookup_compact
+
+            return lookup_compact(idx_array, mask, self._wf_value)  # the reference's four index operations in two passes
         baseline = torch.arange(onv.size(0), device=onv.device, dtype=torch.int64)
         onv_idx = baseline[mask]
         onv_not_idx = baseline[torch.logical_not(mask)]

@@ -244,8 +244,11 @@ def main_simple():
 def main_reduce_sample():
     """Stochastic / semi-stochastic REDUCE goldens (vmc.energy.eloc._reduce_psi of the reference, eps_sample > 0) on the Fe2S2
     integrals, toy ansatz.  torch.multinomial is wrapped so that the draws it returned are stored with the golden: the
-    reference result is a deterministic function of (inputs, draws), which is what the GPU test reproduces."""
+    reference result is a deterministic function of (inputs, draws), which is what the GPU test reproduces.
+    Default dtype = double, as every shipped input sets it (main.py:30, example/Fe2S2/Fe2S2-OO-dcut-20.py:29): with
+    float32 the reference's `_count / eps_sample` (eloc.py:276) is rounded to single precision."""
     torch.set_num_threads(os.cpu_count())
+    torch.set_default_dtype(torch.double)
     ref = load_ref(1)
     libs = types.ModuleType("libs")
     libs.__path__ = []

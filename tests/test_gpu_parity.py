@@ -756,3 +756,80 @@ def test_stochastic_reduce_seeded_generator_is_unbiased_and_reproducible():
     mean, se = draws.mean(0), draws.std(0, ddof=1) / np.sqrt(draws.shape[0])
     assert np.all(se > 0)
     assert np.all(np.abs(mean - g["eloc_real"]) <= 5 * se + 1e-9), (mean - g["eloc_real"], se)
+
+
+# ---- index glue of the lookup: compaction and unique-of-misses ------------------------------
+@pytest.mark.parametrize("n,p_hit", [(0, 0.5), (1, 1.0), (2047, 0.3), (2048, 0.0), (2049, 1.0), (1_000_003, 0.004), (3_000_001, 0.6)])
+@pytest.mark.parametrize("cplx", [False, True])
+def test_lookup_compact_equals_the_references_index_ops(n, p_hit, cplx):
+    g = torch.Generator(device=DEV).manual_seed(n + 17)
+    N = 5000
+    mask = torch.rand(n, generator=g, device=DEV) < p_hit
+    idx = torch.where(mask, torch.randint(0, N, (n,), generator=g, device=DEV), torch.full((n,), -1, device=DEV))
+    val = dev(S.random_psi(N, seed=3, complex_=cplx))
+    hit, miss, value = ops.lookup_compact(idx, mask, val)
+    baseline = torch.arange(n, device=DEV, dtype=torch.int64)  # utils/public_function.py:825-838
+    assert torch.equal(hit, baseline[mask])
+    assert torch.equal(miss, baseline[torch.logical_not(mask)])
+    assert torch.equal(torch.view_as_real(value) if cplx else value, torch.view_as_real(val[idx.masked_select(mask)]) if cplx else val[idx.masked_select(mask)])
+
+
+@pytest.mark.parametrize("L,sorb,na,n", [(1, 40, 15, 50_000), (1, 12, 3, 5000), (2, 100, 25, 3000), (3, 132, 3, 4097), (1, 40, 15, 1), (1, 40, 15, 0)])
+def test_unique_onv_inverse_and_order(L, sorb, na, n):
+    base = S.random_onvs(max(n // 3, 1), sorb, na, na, seed=60 + L)
+    rng = np.random.default_rng(61)
+    x = base[rng.integers(0, base.shape[0], size=n)] if n else base[:0]
+    uniq, inv = ops.unique_onv(dev(x))
+    assert torch.equal(uniq[inv], dev(x))
+    want = np.unique(x, axis=0).shape[0] if n else 0
+    assert uniq.size(0) == want
+    if want > 1:  # strictly ascending as little-endian multi-word integers
+        order = O.sort_onv(uniq.cpu().numpy())
+        assert np.array_equal(order, np.arange(want))
+
+
+def test_func_mirror_matches_the_references_func_semantics():
+    """energy.Func (lookup + unique of the misses + ansatz) against a plain evaluation of every row."""
+    from pynqs_b200.energy import Func
+    from util import toy_amplitude
+
+    f = fe2s2()
+    sorb = f["sorb"]
+    x = dev(f["ci"][:600].copy())
+    comb = ops.get_comb_tensor(x[:3], sorb, f["nele"], f["noA"], f["noB"], False)[0].reshape(-1, 8)
+    rows = torch.cat([comb, comb[:5000], x])  # duplicates among hits and among misses
+    psi_tab = dev(S.random_psi(300, seed=44))
+    lut = WavefunctionLUT(dev(f["ci"][:600:2].copy()), psi_tab, sorb, DEV, rank=0, world_size=1)
+    calls = []
+
+    def ansatz(xx):
+        calls.append(xx.size(0))
+        return toy_amplitude(ops.onv_to_tensor(xx, sorb), sorb, False)
+
+    want = ansatz(rows)
+    found, _, value = lut.lookup(rows)
+    want[found] = value
+    calls.clear()
+    got = Func(ansatz, rows, lut, use_unique=True)
+    assert torch.equal(got, want)
+    n_distinct_misses = np.unique(rows.cpu().numpy()[np.setdiff1d(np.arange(rows.size(0)), found.cpu().numpy())], axis=0).shape[0]
+    assert calls == [n_distinct_misses]  # the ansatz saw every distinct missing determinant exactly once
+    assert torch.equal(Func(ansatz, rows, None, use_unique=True), ansatz(rows))
+
+
+@pytest.mark.parametrize("L,sorb,na,n,m", [(1, 40, 15, 300, 4097), (1, 12, 3, 400, 400), (2, 100, 3, 65, 1000), (3, 132, 3, 10, 513)])
+def test_hij_2d_tiled_matrix_equals_untiled_rows_and_is_symmetric(L, sorb, na, n, m):
+    """2-D get_hij_torch (bra tile in shared memory, one ket per thread) against the 3-D mode, which evaluates the same pairs
+    one by one; for a symmetric Hamiltonian the square matrix is symmetric."""
+    keys = S.random_onvs(max(n, m), sorb, na, na, seed=70 + L)
+    n, m = min(n, keys.shape[0]), min(m, keys.shape[0])
+    h1e, h2e = S.random_packed_integrals(sorb, seed=71, symmetric=True)
+    bra, ket = dev(keys[:n]), dev(keys[:m])
+    H = ops.get_hij_torch(bra, ket, dev(h1e), dev(h2e), sorb, 2 * na)
+    rows = ops.get_hij_torch(bra, ket.unsqueeze(0).expand(n, m, ket.size(1)).contiguous(), dev(h1e), dev(h2e), sorb, 2 * na)
+    assert torch.equal(H, rows)
+    k = min(n, m)
+    assert torch.equal(H[:k, :k], H[:k, :k].T.contiguous())
+    want = O.hij(keys[:4], keys[:m], h1e, h2e, sorb, 2 * na) if hasattr(O, "hij") else None
+    if want is not None:
+        np.testing.assert_array_equal(H[:4].cpu().numpy(), want)
