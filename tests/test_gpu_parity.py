@@ -811,10 +811,12 @@ def test_func_mirror_matches_the_references_func_semantics():
     want[found] = value
     calls.clear()
     got = Func(ansatz, rows, lut, use_unique=True)
-    assert torch.equal(got, want)
+    # (the toy ansatz is a matmul: its last bit depends on the batch it is evaluated in)
+    np.testing.assert_allclose(got.cpu().numpy(), want.cpu().numpy(), rtol=1e-13, atol=0)
+    assert torch.equal(got[found], value)
     n_distinct_misses = np.unique(rows.cpu().numpy()[np.setdiff1d(np.arange(rows.size(0)), found.cpu().numpy())], axis=0).shape[0]
     assert calls == [n_distinct_misses]  # the ansatz saw every distinct missing determinant exactly once
-    assert torch.equal(Func(ansatz, rows, None, use_unique=True), ansatz(rows))
+    np.testing.assert_allclose(Func(ansatz, rows, None, use_unique=True).cpu().numpy(), ansatz(rows).cpu().numpy(), rtol=1e-13, atol=0)
 
 
 @pytest.mark.parametrize("L,sorb,na,n,m", [(1, 40, 15, 300, 4097), (1, 12, 3, 400, 400), (2, 100, 3, 65, 1000), (3, 132, 3, 10, 513)])
