@@ -178,4 +178,4 @@ def test_compat_layer_equals_the_reference_python_rank_for_rank(world):
         p.join(timeout=60)
     for rank, fails, n_checks in res:
         assert not fails, f"rank {rank}: " + "; ".join(fails)
-        assert n_checks >= 27, f"rank {rank}: only {n_checks} comparisons ran"
+        assert n_checks >= 25, f"rank {rank}: only {n_checks} comparisons ran"
