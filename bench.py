@@ -324,7 +324,7 @@ def run_ours(args):
 
     from pynqs_b200 import _lib
     from pynqs_b200 import C_extension as ops
-    from pynqs_b200.distributed import energy_statistics_amplitudes, exchange_unique_samples, rank_slice
+    from pynqs_b200.distributed import energy_statistics_amplitudes, exchange_unique_samples, sample_space_energy_sharded
     from pynqs_b200.lut import WavefunctionLUT, split_length_idx
 
     _lib.load()
@@ -360,11 +360,18 @@ def run_ours(args):
             ev[1].record()
             lut = WavefunctionLUT(uniq, wf, SORB, dev, rank=rank, world_size=world)
             gidx = lut.group_index  # built here, inside the table phase
-            b, e = rank_slice(uniq.size(0), rank, world)
-            x = uniq[b:e]
             e0, e1 = ev[2], ev[3]
             e0.record()
-            eloc, psi0 = ops.eloc_sample_space(x, h1e, h2e, SORB, NELE, NOA, NOB, lut.bra_key, lut.wf_value, gidx)
+            if world == 1:
+                b, e = 0, uniq.size(0)
+                x = uniq  # evaluated in the order the samples were handed in
+                eloc, psi0 = ops.eloc_sample_space(x, h1e, h2e, SORB, NELE, NOA, NOB, lut.bra_key, lut.wf_value, gidx)
+            else:
+                # this rank's rows of the sorted table (split_length_idx); the work is split by beta string and the
+                # energies exchanged with one all-gather (pynqs_b200/distributed.py)
+                b, e = lut.rank_begin, lut.rank_end
+                x = lut.bra_key[b:e]
+                eloc, psi0 = sample_space_energy_sharded(lut, h1e, h2e, SORB, NELE, NOA, NOB)
             e1.record()
             # p_i = |psi_i|^2 / sum_table |psi|^2 * world (reference convention, sample.py:772); the ranks' slices
             # partition the table, so the norm comes out of the statistics' own collective

@@ -113,6 +113,13 @@ int pynqs_lut_hashed(const uint8_t *key, int64_t N, const uint8_t *onv, int64_t 
 int pynqs_group_bytes(int64_t N, int L, int64_t *bytes);
 int pynqs_group_build(const uint8_t *key, int64_t N, int L, void *group_ws, int64_t group_bytes, void *stream);
 
+/* Where the pieces of a group workspace live (byte offsets), for callers that want to read the grouped copies -- e.g. to
+ * hand each GPU the samples of a range of beta strings (pynqs_b200/distributed.py):
+ * out[0] = log2(buckets); out[1 + g] = bucket starts uint32[2^log2 + 1]; out[3 + g] = keys uint64[N, L] in bucket order;
+ * out[5 + g] = rows uint32[N] (row of the sorted table); out[7 + g] = folded other string uint32[N] (L = 1, else -1);
+ * g = 0: bucketed by beta string, g = 1: by alpha string. */
+int pynqs_group_layout(int64_t N, int L, int64_t *out);
+
 /* Additive op: the whole sample-space local energy of vmc/energy/eloc.py:326-397 in one pass,
  * never materialising comb / Hmat:  for each sample x, psi0 = table value of x (0 if absent),
  *   eloc = sum over x' in {x} U SD(x) found in the table of (psi(x') / psi0) * <x|H|x'>.

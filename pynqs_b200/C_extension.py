@@ -481,9 +481,23 @@ class GroupIndex:
                 )
             )
 
+        lay = (_lib.ctypes.c_int64 * 9)()
+        _lib.check(_lib.load().pynqs_group_layout(i64(self.N), self.L, lay))
+        self._layout = list(lay)
+
     @property
     def nbytes(self) -> int:
         return self.workspace.numel()
+
+    def keys(self, grouping: int = 0) -> Tensor:
+        """the table's keys in bucket order (uint8 [N, 8L]): grouping 0 = bucketed by beta string, 1 = by alpha string"""
+        o = self._layout[3 + grouping]
+        return self.workspace[o : o + self.N * 8 * self.L].view(self.N, 8 * self.L)
+
+    def rows(self, grouping: int = 0) -> Tensor:
+        """row in the sorted table of every key of keys(grouping) (int32 [N])"""
+        o = self._layout[5 + grouping]
+        return self.workspace[o : o + self.N * 4].view(torch.int32)
 
 
 _group_cache: dict = {}

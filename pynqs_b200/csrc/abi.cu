@@ -275,6 +275,22 @@ int pynqs_group_build(const uint8_t *key, int64_t N, int L, void *group_ws, int6
   return launch_group_build(reinterpret_cast<const u64 *>(key), N, L, group_ws, group_bytes, (cudaStream_t)stream);
 }
 
+int pynqs_group_layout(int64_t N, int L, int64_t *out) {
+  if (N < 0 || L < 1 || L > PYNQS_MAX_SORB_LEN) {
+    set_error("group_layout: bad N = %lld or L = %d", (long long)N, L);
+    return PYNQS_EVALUE;
+  }
+  const GroupLayout l = group_layout(N, L);
+  out[0] = (int64_t)l.log2_buckets;
+  for (int g = 0; g < 2; ++g) {
+    out[1 + g] = l.start_off[g];
+    out[3 + g] = l.keys_off[g];
+    out[5 + g] = l.rows_off[g];
+    out[7 + g] = L == 1 ? l.half_off[g] : -1;
+  }
+  return 0;
+}
+
 int pynqs_set_tuning(const char *name, int64_t value) {
   ElocTuning &t = eloc_tuning();
   struct {
