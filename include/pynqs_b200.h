@@ -113,6 +113,12 @@ int pynqs_lut_hashed(const uint8_t *key, int64_t N, const uint8_t *onv, int64_t 
 int pynqs_group_bytes(int64_t N, int L, int64_t *bytes);
 int pynqs_group_build(const uint8_t *key, int64_t N, int L, void *group_ws, int64_t group_bytes, void *stream);
 
+/* Placement tier for integrals that do not stay in L2 on their own (reference: plain global loads,
+ * cpp_src/cuda/hamiltonian.cu:9-34): set aside persisting L2 (up to the device maximum) and attach an access-policy window
+ * over [ptr, ptr + bytes) to `stream`; kernels launched on it afterwards keep that range resident.  hit_ratio <= 0 picks
+ * carve-out / window.  granted[0] = bytes set aside, granted[1] = window bytes (may be NULL).  ptr == NULL resets. */
+int pynqs_l2_persist(const void *ptr, int64_t bytes, double hit_ratio, void *stream, int64_t *granted);
+
 /* Where the pieces of a group workspace live (byte offsets), for callers that want to read the grouped copies -- e.g. to
  * hand each GPU the samples of a range of beta strings (pynqs_b200/distributed.py):
  * out[0] = log2(buckets); out[1 + g] = bucket starts uint32[2^log2 + 1]; out[3 + g] = keys uint64[N, L] in bucket order;

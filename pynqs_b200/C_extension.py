@@ -191,6 +191,18 @@ class PreparedIntegrals:
         return self.workspace.numel()
 
 
+def pin_in_l2(t: "Tensor | None", hit_ratio: float = 0.0) -> Tuple[int, int]:
+    """Keep a tensor (h2e, a PreparedIntegrals workspace, a table copy) resident in a persisting-L2 window for the kernels
+    launched afterwards on the current stream; pin_in_l2(None) lifts it.  Returns (bytes set aside, window bytes).
+    For Hamiltonians too large to stay in L2 by themselves next to the streaming outputs (H50: 98 MB of h2e)."""
+    dev = torch.device("cuda", torch.cuda.current_device()) if t is None else _need_cuda(t)
+    granted = (_lib.ctypes.c_int64 * 2)()
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().pynqs_l2_persist(vp(None if t is None else t.data_ptr()), i64(0 if t is None else t.numel() * t.element_size()),
+                                               _lib.ctypes.c_double(float(hit_ratio)), _stream(dev), granted))
+    return int(granted[0]), int(granted[1])
+
+
 _prep_cache: dict = {}
 # preparing costs one pass over ~(sorb/2)^4 elements: only worth it when the call writes more than that
 _PREP_MIN_OUTPUT_RATIO = 4

@@ -275,6 +275,45 @@ int pynqs_group_build(const uint8_t *key, int64_t N, int L, void *group_ws, int6
   return launch_group_build(reinterpret_cast<const u64 *>(key), N, L, group_ws, group_bytes, (cudaStream_t)stream);
 }
 
+// h2e placement tier for Hamiltonians that neither fit shared memory nor stay in L2 on their own (north_star: "pinned in a
+// persisting-L2 window"): carve persisting L2 out of the cache and mark [ptr, ptr + bytes) as persisting for the work
+// launched on `stream` afterwards.  hit_ratio < 1 keeps a window larger than the carve-out from thrashing itself.
+int pynqs_l2_persist(const void *ptr, int64_t bytes, double hit_ratio, void *stream, int64_t *granted) {
+  int dev = 0;
+  cudaDeviceProp prop;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return check_launch("l2_persist: device query");
+  cudaStreamAttrValue attr;
+  memset(&attr, 0, sizeof(attr));
+  if (ptr == nullptr || bytes <= 0) {  // reset: no window, persisting lines back to normal
+    attr.accessPolicyWindow.num_bytes = 0;
+    attr.accessPolicyWindow.hitProp = cudaAccessPropertyNormal;
+    attr.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+    cudaStreamSetAttribute((cudaStream_t)stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+    cudaCtxResetPersistingL2Cache();
+    if (granted) *granted = 0;
+    return check_launch("l2_persist reset");
+  }
+  size_t carve = (size_t)prop.persistingL2CacheMaxSize;
+  if ((size_t)bytes < carve) carve = (size_t)bytes;
+  if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve) != cudaSuccess) return check_launch("l2_persist: set-aside");
+  size_t win = (size_t)bytes;
+  if (win > (size_t)prop.accessPolicyMaxWindowSize) win = (size_t)prop.accessPolicyMaxWindowSize;
+  attr.accessPolicyWindow.base_ptr = const_cast<void *>(ptr);
+  attr.accessPolicyWindow.num_bytes = win;
+  double ratio = hit_ratio > 0.0 ? hit_ratio : (double)carve / (double)win;
+  if (ratio > 1.0) ratio = 1.0;
+  attr.accessPolicyWindow.hitRatio = (float)ratio;
+  attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+  attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+  if (cudaStreamSetAttribute((cudaStream_t)stream, cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess)
+    return check_launch("l2_persist: access policy window");
+  if (granted) {
+    granted[0] = (int64_t)carve;
+    granted[1] = (int64_t)win;
+  }
+  return 0;
+}
+
 int pynqs_group_layout(int64_t N, int L, int64_t *out) {
   if (N < 0 || L < 1 || L > PYNQS_MAX_SORB_LEN) {
     set_error("group_layout: bad N = %lld or L = %d", (long long)N, L);
