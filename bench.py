@@ -328,6 +328,10 @@ def run_ours(args):
     from pynqs_b200.lut import WavefunctionLUT, split_length_idx
 
     _lib.load()
+    from pynqs_b200 import peer
+
+    if args.no_peer:
+        peer.set_enabled(False)
     h1e_np, h2e_np, integrals = load_integrals()
     h1e, h2e = torch.from_numpy(h1e_np).to(dev), torch.from_numpy(h2e_np).to(dev)
     M = ops.get_Num_SinglesDoubles(SORB, NOA, NOB) + 1
@@ -484,6 +488,7 @@ def run_ours(args):
         return
     cfg = base_config(n_total, integrals)
     cfg.update({"method": "sample-space, one-pass kernels", "l2": "flushed between timed steps (512 MiB write)",
+                "collectives": peer.route() if world > 1 else "none (one rank)",
                 "parallelism": f"samples sharded over {world} rank(s)", "step": "exchange + table sort + grouped table + E_loc + statistics"})
     line = {
         "metric": METRIC, "value": main["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -621,6 +626,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-api-path", action="store_true")
     ap.add_argument("--no-variants", action="store_true")
+    ap.add_argument("--no-peer", action="store_true", help="NCCL collectives only (no NVLink peer-memory pull kernels)")
     args = ap.parse_args()
     if args.impl != "ours":
         run_reference_arm(args)

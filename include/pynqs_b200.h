@@ -113,6 +113,18 @@ int pynqs_lut_hashed(const uint8_t *key, int64_t N, const uint8_t *onv, int64_t 
 int pynqs_group_bytes(int64_t N, int L, int64_t *bytes);
 int pynqs_group_build(const uint8_t *key, int64_t N, int L, void *group_ws, int64_t group_bytes, void *stream);
 
+/* ---- multi-GPU: pull collectives over NVLink peer memory (replace the all_gathers of vmc/sample.py:652-721) -----------
+ * peer_ptrs: DEVICE array of `world` pointers, entry k = rank k's symmetric buffer as mapped into this process (e.g.
+ * torch.distributed._symmetric_memory: handle.buffer_ptrs_dev).  The caller brackets the calls with barriers (data
+ * published before, buffers free to overwrite after).
+ *   pynqs_peer_gather     : out[k * bytes_per_rank + j] = peer k's byte src_offset + j, j < bytes_per_rank (multiples of 16);
+ *   pynqs_peer_gather_rows: the peers' pieces (total elements split like split_length_idx: the first total % world pieces one
+ *                           longer), piece k at src_offset of peer k; out[i] = element pos[i] of their concatenation.
+ *                           elem_bytes 8 or 16. */
+int pynqs_peer_gather(const void *const *peer_ptrs, int world, int64_t src_offset, int64_t bytes_per_rank, void *out, void *stream);
+int pynqs_peer_gather_rows(const void *const *peer_ptrs, int world, int64_t src_offset, const uint32_t *pos, int64_t n, int64_t total,
+                           int elem_bytes, void *out, void *stream);
+
 /* Placement tier for integrals that do not stay in L2 on their own (reference: plain global loads,
  * cpp_src/cuda/hamiltonian.cu:9-34): set aside persisting L2 (up to the device maximum) and attach an access-policy window
  * over [ptr, ptr + bytes) to `stream`; kernels launched on it afterwards keep that range resident.  hit_ratio <= 0 picks
@@ -123,7 +135,8 @@ int pynqs_l2_persist(const void *ptr, int64_t bytes, double hit_ratio, void *str
  * hand each GPU the samples of a range of beta strings (pynqs_b200/distributed.py):
  * out[0] = log2(buckets); out[1 + g] = bucket starts uint32[2^log2 + 1]; out[3 + g] = keys uint64[N, L] in bucket order;
  * out[5 + g] = rows uint32[N] (row of the sorted table); out[7 + g] = folded other string uint32[N] (L = 1, else -1);
- * g = 0: bucketed by beta string, g = 1: by alpha string. */
+ * g = 0: bucketed by beta string, g = 1: by alpha string.  out[9] = position uint32[N] of every row of the sorted table in
+ * the beta-grouped copy (the inverse of rows, g = 0).  out: int64[10]. */
 int pynqs_group_layout(int64_t N, int L, int64_t *out);
 
 /* Additive op: the whole sample-space local energy of vmc/energy/eloc.py:326-397 in one pass,

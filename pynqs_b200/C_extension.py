@@ -493,7 +493,7 @@ class GroupIndex:
                 )
             )
 
-        lay = (_lib.ctypes.c_int64 * 9)()
+        lay = (_lib.ctypes.c_int64 * 10)()
         _lib.check(_lib.load().pynqs_group_layout(i64(self.N), self.L, lay))
         self._layout = list(lay)
 
@@ -505,6 +505,11 @@ class GroupIndex:
         """the table's keys in bucket order (uint8 [N, 8L]): grouping 0 = bucketed by beta string, 1 = by alpha string"""
         o = self._layout[3 + grouping]
         return self.workspace[o : o + self.N * 8 * self.L].view(self.N, 8 * self.L)
+
+    def pos(self) -> Tensor:
+        """position in keys(0) of every row of the sorted table (int32 [N]): the inverse of rows(0)"""
+        o = self._layout[9]
+        return self.workspace[o : o + self.N * 4].view(torch.int32)
 
     def rows(self, grouping: int = 0) -> Tensor:
         """row in the sorted table of every key of keys(grouping) (int32 [N])"""

@@ -19,7 +19,7 @@ SYMBOLS = [
     "pynqs_reduce_sample_scratch_bytes", "pynqs_reduce_sample_count", "pynqs_reduce_sample_emit",
     "pynqs_compact_scratch_bytes", "pynqs_lookup_count", "pynqs_lookup_emit", "pynqs_unique_count", "pynqs_unique_emit",
     "pynqs_merge_rank_sample", "pynqs_sort_bytes", "pynqs_sort_table", "pynqs_moments_scratch_bytes", "pynqs_weighted_moments",
-    "pynqs_set_tuning", "pynqs_l2_persist", "pynqs_launch_count",
+    "pynqs_peer_gather", "pynqs_peer_gather_rows", "pynqs_set_tuning", "pynqs_l2_persist", "pynqs_launch_count",
 ]
 
 OK, EVALUE, EOVERFLOW, ECUDA, EWORKSPACE = 0, 1, 2, 3, 4

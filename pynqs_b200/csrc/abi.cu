@@ -73,6 +73,8 @@ int launch_lookup_emit(const unsigned char *, const long long *, long long, cons
                        cudaStream_t);
 int launch_unique_count(const u64 *, long long, int, void *, long long, unsigned long long *, cudaStream_t);
 int launch_unique_emit(const u64 *, const long long *, long long, int, void *, u64 *, long long *, cudaStream_t);
+int launch_peer_gather(const void *const *, int, long long, long long, void *, cudaStream_t);
+int launch_peer_gather_rows(const void *const *, long long, const u32 *, long long, long long, int, int, void *, cudaStream_t);
 int launch_merge_counts(const long long *, const long long *, long long, long long, long long *, cudaStream_t);
 int launch_onv_to_tensor(const u64 *, void *, int, long long, int, cudaStream_t);
 int launch_tensor_to_onv(const unsigned char *, unsigned char *, long long, int, cudaStream_t);
@@ -314,6 +316,23 @@ int pynqs_l2_persist(const void *ptr, int64_t bytes, double hit_ratio, void *str
   return 0;
 }
 
+int pynqs_peer_gather(const void *const *peer_ptrs, int world, int64_t src_offset, int64_t bytes_per_rank, void *out, void *stream) {
+  if (peer_ptrs == nullptr || world < 1 || bytes_per_rank < 0 || src_offset < 0) {
+    set_error("peer_gather: bad arguments");
+    return PYNQS_EVALUE;
+  }
+  return launch_peer_gather(peer_ptrs, world, src_offset, bytes_per_rank, out, (cudaStream_t)stream);
+}
+
+int pynqs_peer_gather_rows(const void *const *peer_ptrs, int world, int64_t src_offset, const uint32_t *pos, int64_t n, int64_t total,
+                           int elem_bytes, void *out, void *stream) {
+  if (peer_ptrs == nullptr || world < 1 || n < 0 || total < world || src_offset < 0) {
+    set_error("peer_gather_rows: bad arguments");
+    return PYNQS_EVALUE;
+  }
+  return launch_peer_gather_rows(peer_ptrs, src_offset, pos, n, total, world, elem_bytes, out, (cudaStream_t)stream);
+}
+
 int pynqs_group_layout(int64_t N, int L, int64_t *out) {
   if (N < 0 || L < 1 || L > PYNQS_MAX_SORB_LEN) {
     set_error("group_layout: bad N = %lld or L = %d", (long long)N, L);
@@ -327,6 +346,7 @@ int pynqs_group_layout(int64_t N, int L, int64_t *out) {
     out[5 + g] = l.rows_off[g];
     out[7 + g] = L == 1 ? l.half_off[g] : -1;
   }
+  out[9] = l.pos_off;
   return 0;
 }
 

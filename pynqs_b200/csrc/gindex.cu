@@ -35,6 +35,8 @@ GroupLayout group_layout(long long N, int L) {
     l.half_off[g] = o;
     if (L == 1) o = up(o + N * 4);
   }
+  l.pos_off = o;
+  o = up(o + N * 4);
   l.scratch_off = o;
   for (int g = 0; g < 2; ++g)
     for (int k = 0; k < 2; ++k) {
@@ -65,6 +67,7 @@ GroupView group_view(const void *ws, long long N, int L) {
     v.rows[g] = reinterpret_cast<const u32 *>(b + l.rows_off[g]);
     v.half[g] = L == 1 ? reinterpret_cast<const u32 *>(b + l.half_off[g]) : nullptr;
   }
+  v.pos = reinterpret_cast<const u32 *>(b + l.pos_off);
   v.shift = 32u - l.log2_buckets;
   return v;
 }
@@ -93,7 +96,7 @@ __global__ void __launch_bounds__(256)
 group_finish_kernel(const u64 *__restrict__ key, long long N, u32 log2_buckets, const u32 *__restrict__ bktB,
                     const u32 *__restrict__ bktA, const u32 *__restrict__ rowsB, const u32 *__restrict__ rowsA, u64 *__restrict__ keysB,
                     u64 *__restrict__ keysA, u32 *__restrict__ startB, u32 *__restrict__ startA, u32 *__restrict__ halfB,
-                    u32 *__restrict__ halfA) {
+                    u32 *__restrict__ halfA, u32 *__restrict__ posB) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
   const bool ga = blockIdx.y != 0;
@@ -102,6 +105,7 @@ group_finish_kernel(const u64 *__restrict__ key, long long N, u32 log2_buckets, 
   u64 *keys = ga ? keysA : keysB;
   u32 *start = ga ? startA : startB;
   const u32 row = rows[i];
+  if (!ga) posB[row] = (u32)i;  // where the beta-grouped copy keeps every table row
 #pragma unroll
   for (int w = 0; w < L; ++w) keys[i * L + w] = key[(long long)row * L + w];
   if (L == 1) {  // the other string of the key, folded
@@ -177,6 +181,7 @@ int launch_group_build(const u64 *key, long long N, int L, void *ws, long long w
                     {reinterpret_cast<u32 *>(b + l.bkt_off[1][0]), reinterpret_cast<u32 *>(b + l.bkt_off[1][1])}};
   u32 *iota = reinterpret_cast<u32 *>(b + l.iota_off);
   u32 *half[2] = {reinterpret_cast<u32 *>(b + l.half_off[0]), reinterpret_cast<u32 *>(b + l.half_off[1])};
+  u32 *posB = reinterpret_cast<u32 *>(b + l.pos_off);
   if (cudaMemsetAsync(hdr, 0, sizeof(GroupHeader), st) != cudaSuccess) return check_launch("group header memset");
   if (N == 0) {
     group_empty_kernel<<<148, 256, 0, st>>>(hdr, l.log2_buckets, start[0], start[1]);
@@ -213,7 +218,7 @@ int launch_group_build(const u64 *key, long long N, int L, void *ws, long long w
   const dim3 grid(blocks, 2);
 #define PYNQS_FINISH(LL)                                                                                                           \
   group_finish_kernel<LL><<<grid, 256, 0, st>>>(key, N, l.log2_buckets, bkt[0][1], bkt[1][1], rows[0], rows[1], keys[0], keys[1], \
-                                                start[0], start[1], half[0], half[1])
+                                                start[0], start[1], half[0], half[1], posB)
   switch (L) {
     case 1: PYNQS_FINISH(1); break;
     case 2: PYNQS_FINISH(2); break;

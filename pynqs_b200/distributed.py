@@ -21,6 +21,7 @@ import torch
 import torch.distributed as dist
 from torch import Tensor
 
+from . import peer
 from .lut import WavefunctionLUT, split_length_idx
 
 
@@ -64,9 +65,12 @@ def exchange_unique_samples(onv: Tensor, psi: Tensor, counts: Optional[Tensor] =
             cols.append(counts.to(torch.int64).contiguous())
         if ragged:
             cols = [torch.cat([t, t.new_zeros((n_max - n_r,) + tuple(t.shape[1:]))]) if n_r < n_max else t for t in cols]
-        outs = [torch.empty((world * n_max,) + tuple(t.shape[1:]), dtype=t.dtype, device=dev) for t in cols]
-        for o, t in zip(outs, cols):
-            dist.all_gather_into_tensor(o, t)
+        # NVLink peer memory when it can be set up (one pull kernel per column between two barriers), else NCCL
+        outs = peer.all_gather_columns(cols, n_max) if dev.type == "cuda" else None
+        if outs is None:
+            outs = [torch.empty((world * n_max,) + tuple(t.shape[1:]), dtype=t.dtype, device=dev) for t in cols]
+            for o, t in zip(outs, cols):
+                dist.all_gather_into_tensor(o, t)
         if ragged:  # drop the padding rows
             outs = [torch.cat([o[r * n_max : r * n_max + n_list[r]] for r in range(world)]) for o in outs]
         all_onv = outs[0]
@@ -119,10 +123,20 @@ def sample_space_energy_sharded(lut: WavefunctionLUT, h1e: Tensor, h2e: Tensor, 
         return ops.eloc_sample_space(lut.bra_key, h1e, h2e, sorb, nele, noa, nob, lut.bra_key, lut.wf_value, gi)
     ends = [0] + split_length_idx(N, world)
     n_max = max(ends[k + 1] - ends[k] for k in range(world))
-    keys_b, rows_b = gi.keys(0), gi.rows(0)
-    mine = keys_b[ends[rank] : ends[rank + 1]]
+    mine = gi.keys(0)[ends[rank] : ends[rank + 1]]
     eloc_part, _ = ops.eloc_sample_space(mine, h1e, h2e, sorb, nele, noa, nob, lut.bra_key, lut.wf_value, gi)
     cplx = eloc_part.is_complex()
+    area = peer.PeerExchange.get(n_max * eloc_part.element_size(), eloc_part.device)
+    if area is not None:
+        # publish this rank's energies, then pull exactly the rows this rank owns out of the peers' memory (csrc/peer.cu):
+        # 1/W of the data moves and no all-gathered copy is stored
+        area.local(0, eloc_part.numel() * eloc_part.element_size()).copy_(eloc_part.view(torch.float64).view(torch.uint8) if not cplx
+                                                                           else torch.view_as_real(eloc_part).reshape(-1).view(torch.uint8))
+        area.barrier()
+        eloc = torch.empty(e - b, dtype=eloc_part.dtype, device=eloc_part.device)
+        area.gather_rows(0, gi.pos()[b:e], N, eloc)
+        area.barrier()
+        return eloc, lut.wf_value[b:e]
     send = torch.view_as_real(eloc_part) if cplx else eloc_part
     if send.size(0) < n_max:
         send = torch.cat([send, send.new_zeros((n_max - send.size(0),) + tuple(send.shape[1:]))])
@@ -130,10 +144,8 @@ def sample_space_energy_sharded(lut: WavefunctionLUT, h1e: Tensor, h2e: Tensor, 
     dist.all_gather_into_tensor(recv, send.contiguous())
     if n_max * world != N:  # ragged: drop the padding rows
         recv = torch.cat([recv[k * n_max : k * n_max + ends[k + 1] - ends[k]] for k in range(world)])
-    # recv is in grouped order; position of every table row in that order, then this rank's rows
-    pos = torch.empty(N, dtype=torch.int64, device=recv.device)
-    pos[rows_b.to(torch.int64)] = torch.arange(N, dtype=torch.int64, device=recv.device)
-    eloc = recv[pos[b:e]]
+    # recv is in grouped order; the group index knows where that order keeps every table row: this rank's rows
+    eloc = recv[gi.pos()[b:e]]
     return (torch.view_as_complex(eloc.contiguous()) if cplx else eloc), lut.wf_value[b:e]
 
 
