@@ -326,6 +326,7 @@ def run_ours(args):
     from pynqs_b200 import C_extension as ops
     from pynqs_b200.distributed import energy_statistics_amplitudes, exchange_unique_samples, sample_space_energy_sharded
     from pynqs_b200.lut import WavefunctionLUT, split_length_idx
+    from pynqs_b200.step import SampleSpaceStep
 
     _lib.load()
     from pynqs_b200 import peer
@@ -338,58 +339,32 @@ def run_ours(args):
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
 
     def measure(keys_np, psi_np, steps, warmup, want_e2e=True):
-        """Times `steps` steps of the hot path over the sample set (keys_np, psi_np); returns a dict of the
-        timings plus this rank's E_loc of the last step (device tensor, sorted-table order) and the sort permutation."""
+        """Times `steps` steps of the hot path over the sample set (keys_np, psi_np).  The timed step is the library's
+        SampleSpaceStep (pynqs_b200/step.py): exchange -> table -> E_loc -> statistics captured in ONE CUDA graph after the
+        warm-up steps and replayed per step (--no-graph: launched kernel by kernel).  A few extra EAGER steps with CUDA events
+        between the phases give `phases_ms_rank0` (not part of `value`)."""
         n_total = keys_np.shape[0]
         cplx = np.iscomplexobj(psi_np)
         # every rank "samples" a contiguous piece of the unique set (disjoint pieces, like use_same_tree)
         cuts = [0] + split_length_idx(n_total, world)
         lo, hi = cuts[rank], cuts[rank + 1]
+        if n_total % world:
+            raise SystemExit("bench.py: --samples must be a multiple of the number of ranks")
         host_keys = torch.from_numpy(keys_np[lo:hi]).pin_memory()
         host_psi = torch.from_numpy(psi_np[lo:hi]).pin_memory()
         d_keys, d_psi = host_keys.to(dev), host_psi.to(dev)
-        host_eloc = torch.empty(hi - lo + 1, dtype=d_psi.dtype).pin_memory()
-        kern_ms, phase_ev, keep = [], [], {}
-        equal_sizes = n_total % world == 0
+        host_eloc = torch.empty(hi - lo, dtype=d_psi.dtype).pin_memory()
+        step_obj = SampleSpaceStep(hi - lo, d_keys.size(1), d_psi.dtype, h1e, h2e, SORB, NELE, NOA, NOB, device=dev,
+                                   use_graph=not args.no_graph, warmup=max(2, warmup - 1))
+        step_obj.load(d_keys, d_psi)
 
         def step(from_host: bool):
-            ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
-            ev[0].record()
             if from_host:
-                k = host_keys.to(dev, non_blocking=True)
-                p = host_psi.to(dev, non_blocking=True)
-            else:
-                k, p = d_keys, d_psi
-            uniq, wf, cnt = exchange_unique_samples(k, p, None, disjoint=True, equal_sizes=equal_sizes)
-            ev[1].record()
-            lut = WavefunctionLUT(uniq, wf, SORB, dev, rank=rank, world_size=world)
-            gidx = lut.group_index  # built here, inside the table phase
-            e0, e1 = ev[2], ev[3]
-            e0.record()
-            if world == 1:
-                b, e = 0, uniq.size(0)
-                x = uniq  # evaluated in the order the samples were handed in
-                eloc, psi0 = ops.eloc_sample_space(x, h1e, h2e, SORB, NELE, NOA, NOB, lut.bra_key, lut.wf_value, gidx)
-            else:
-                # this rank's rows of the sorted table (split_length_idx); the work is split by beta string and the
-                # energies exchanged with one all-gather (pynqs_b200/distributed.py)
-                b, e = lut.rank_begin, lut.rank_end
-                x = lut.bra_key[b:e]
-                eloc, psi0 = sample_space_energy_sharded(lut, h1e, h2e, SORB, NELE, NOA, NOB)
-            e1.record()
-            # p_i = |psi_i|^2 / sum_table |psi|^2 * world (reference convention, sample.py:772); the ranks' slices
-            # partition the table, so the norm comes out of the statistics' own collective
-            # (the collective is issued inside the step; the host read of its 7 doubles per rank happens after the
-            #  timed region -- except end to end, where reading the result back IS part of the step)
-            st = energy_statistics_amplitudes(eloc, psi0, lazy=True)
+                step_obj.load(host_keys, host_psi)  # H2D of this step's inputs (pinned memory)
+            eloc, psi0, st = step_obj.run()
             if from_host:
-                host_eloc[: e - b].copy_(eloc, non_blocking=True)
+                host_eloc.copy_(eloc, non_blocking=True)  # D2H of the step's result
                 st = st.result()
-            ev[4].record()
-            kern_ms.append((e0, e1, e - b))
-            if not from_host:
-                phase_ev.append(ev)
-            keep["eloc"], keep["x"], keep["lut"] = eloc, x, lut
             return st
 
         def timed(n_steps: int, from_host: bool):
@@ -411,33 +386,58 @@ def run_ours(args):
                 dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             return float(tt.item()), st
 
-        for _ in range(warmup):
+        for _ in range(max(warmup, 4)):  # eager steps, then the capture, then replays
             step(False)
         torch.cuda.synchronize()
-        kern_ms.clear()
-        phase_ev.clear()
         l0 = _lib.launch_count()
         total_ms, st = timed(steps, False)
         launches = _lib.launch_count() - l0
-        kern = [(a.elapsed_time(b), n) for a, b, n in kern_ms]
+        if step_obj.graph is not None:  # replays do not pass through the library's launch counter: count one eager step
+            l0 = _lib.launch_count()
+            step_obj._body()
+            launches = (_lib.launch_count() - l0) * steps
         out = {"n_total": n_total, "ms_per_step": total_ms / steps, "value": n_total / (total_ms / steps * 1e-3), "launches": int(launches),
-               "kernel_ms": sum(t for t, _ in kern) / len(kern), "kernel_samples": kern[0][1], "stats": st.result() if hasattr(st, "result") else st,
-               "cplx": cplx}
-        names = ["exchange", "table_sort_and_index", "eloc_kernels", "probabilities_and_statistics"]
-        out["phases"] = {nm: sum(ev[i].elapsed_time(ev[i + 1]) for ev in phase_ev) / len(phase_ev) for i, nm in enumerate(names)}
+               "stats": st.result(), "cplx": cplx, "graph": step_obj.graph is not None, "why_eager": step_obj.why_eager}
         if want_e2e:
-            for _ in range(min(warmup, 2)):  # the end-to-end path has first-use costs of its own (pinned copies both ways)
+            for _ in range(2):  # the end-to-end path has first-use costs of its own (pinned copies both ways)
                 step(True)
             torch.cuda.synchronize()
             e2e_ms, st2 = timed(steps, True)
-            st2 = st2.result() if hasattr(st2, "result") else st2
             out["e2e"] = {"value": n_total / (e2e_ms / steps * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(n_total * (8 + d_psi.element_size())),
-                          "d2h_bytes_per_step": int(n_total * d_psi.element_size() + 40 * world), "ms_per_step": e2e_ms / steps}
+                          "d2h_bytes_per_step": int(n_total * d_psi.element_size() + 56 * world), "ms_per_step": e2e_ms / steps}
             out["mean_e2e"] = st2["mean"]
-        # E_loc of this rank's slice back in the ORIGINAL sample order (rank 0 at N = 1 only: parity legs)
-        # (the samples are evaluated in the order they were handed in, not in the table's sorted order)
+        # the phases of the step, from eager launches with events in between (kernel by kernel, so launch-latency bound at
+        # small per-rank sizes; the timed value above is the captured step)
+        names = ["exchange", "table_sort_and_index", "eloc_kernels", "probabilities_and_statistics"]
+        acc, k_ms, nphase = [0.0] * 4, 0.0, 3
+        for _ in range(nphase):
+            flush.fill_(1)
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+            ev[0].record()
+            uniq, wf, _ = exchange_unique_samples(d_keys, d_psi, None, disjoint=True, equal_sizes=True)
+            ev[1].record()
+            lut = WavefunctionLUT(uniq, wf, SORB, dev, rank=rank, world_size=world)
+            lut.group_index  # built here, inside the table phase
+            ev[2].record()
+            eloc, psi0 = sample_space_energy_sharded(lut, h1e, h2e, SORB, NELE, NOA, NOB)
+            ev[3].record()
+            energy_statistics_amplitudes(eloc, psi0, lazy=True)
+            ev[4].record()
+            torch.cuda.synchronize()
+            for i in range(4):
+                acc[i] += ev[i].elapsed_time(ev[i + 1]) / nphase
+        out["phases"] = dict(zip(names, acc))
+        out["kernel_ms"], out["kernel_samples"] = acc[2], hi - lo
+        # E_loc of the whole sample set back in the ORIGINAL sample order (one rank only: parity legs).  The step returns the
+        # rows of the sorted table; row j of it is original row sort_perm[j]
         if world == 1:
-            out["eloc_orig"] = keep["eloc"].cpu().numpy()
+            eloc_sorted, _, _ = step_obj.run()
+            eloc_orig = torch.empty_like(eloc_sorted)
+            eloc_orig[step_obj.lut._sort_perm] = eloc_sorted
+            out["eloc_orig"] = eloc_orig.cpu().numpy()
         out["d_keys"], out["d_psi"] = d_keys, d_psi
         return out
 
@@ -489,6 +489,7 @@ def run_ours(args):
     cfg = base_config(n_total, integrals)
     cfg.update({"method": "sample-space, one-pass kernels", "l2": "flushed between timed steps (512 MiB write)",
                 "collectives": peer.route() if world > 1 else "none (one rank)",
+                "launch": "one CUDA graph per step (captured after the warm-up steps)" if main["graph"] else "kernel by kernel: " + main["why_eager"],
                 "parallelism": f"samples sharded over {world} rank(s)", "step": "exchange + table sort + grouped table + E_loc + statistics"})
     line = {
         "metric": METRIC, "value": main["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -626,6 +627,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-api-path", action="store_true")
     ap.add_argument("--no-variants", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch the step kernel by kernel instead of replaying its CUDA graph")
     ap.add_argument("--no-peer", action="store_true", help="NCCL collectives only (no NVLink peer-memory pull kernels)")
     args = ap.parse_args()
     if args.impl != "ours":

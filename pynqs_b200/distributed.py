@@ -120,7 +120,9 @@ def sample_space_energy_sharded(lut: WavefunctionLUT, h1e: Tensor, h2e: Tensor, 
     N = lut.bra_key.size(0)
     b, e = lut.rank_begin, lut.rank_end
     if world == 1:
-        return ops.eloc_sample_space(lut.bra_key, h1e, h2e, sorb, nele, noa, nob, lut.bra_key, lut.wf_value, gi)
+        # one rank: the whole table, evaluated in the beta-grouped order (the samples of a beta string next to each other)
+        eloc_b, _ = ops.eloc_sample_space(gi.keys(0), h1e, h2e, sorb, nele, noa, nob, lut.bra_key, lut.wf_value, gi)
+        return eloc_b[gi.pos()], lut.wf_value
     ends = [0] + split_length_idx(N, world)
     n_max = max(ends[k + 1] - ends[k] for k in range(world))
     mine = gi.keys(0)[ends[rank] : ends[rank + 1]]
