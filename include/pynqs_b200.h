@@ -234,7 +234,8 @@ int pynqs_weighted_moments(const void *eloc, int eloc_complex, const void *weigh
  * a group is searched instead of walked, default 64), "full_keys" (1: one-word ONVs take the full-key route of
  * multi-word ONVs), "block_enable" (0: per-sample kernel only), "block_min_samples" (calls with fewer samples use the
  * per-sample kernel only, default 4096), "block_min_group" (samples sharing a beta string needed for a tile of the
- * block kernel, default 8).  name == NULL restores every default.  The scratch size of pynqs_eloc_scratch_bytes
+ * block kernel, default 8), "eval_tiles" (evaluation kernel: 0 one warp per sample, 1 = default: 32 samples per warp for
+ * large calls, 2: for every call).  name == NULL restores every default.  The scratch size of pynqs_eloc_scratch_bytes
  * depends on the knobs: set them before sizing the scratch. */
 int pynqs_set_tuning(const char *name, int64_t value);
 

@@ -37,6 +37,7 @@ struct ElocTuning {
   int block_min_samples = 4096;  // calls with fewer samples go to the per-sample kernel only
   int block_min_group = 8;     // samples sharing a beta string needed for a tile of the block kernel
   int block_enable = 1;
+  int eval_tiles = 1;          // 1: large calls evaluate 32 samples per warp; 2: every call does; 0: one warp per sample
 };
 ElocTuning &eloc_tuning();
 

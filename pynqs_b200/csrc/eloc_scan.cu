@@ -750,6 +750,198 @@ eloc_eval_kernel(const u64 *__restrict__ bra, long long n, const double *__restr
   }
 }
 
+// ---- evaluation, 32 samples per warp -------------------------------------------------------------------------------------
+// The kernel above gives a sample a whole warp: with ~33 hits per sample its second pass over the hit list runs with one
+// lane.  Here a warp takes a TILE of 32 consecutive samples (lane l keeps sample l's bookkeeping) and walks the hit lists of
+// all of them back to back, 32 hits per pass whatever sample they belong to: ~1 000 hits = ~33 full passes instead of 64 half
+// empty ones.  The products (psi'/psi0) * H of a pass are summed per sample with a segmented shuffle scan (the hits of a
+// sample are adjacent) and the segment tails add into the sample's accumulator in shared memory -- a fixed order, no atomics.
+// Runs: round r of the outer loop takes run r of every sample of the tile (one or two rounds after the block kernel).
+// Samples flagged for the reference's route (overflow, duplicate keys) are then handled one by one by the whole warp.
+struct EvalTileSmem {
+  u64 x[32][kMaxL];
+  double p0[32][2];
+  double acc[32][2];
+};
+
+template <int L, bool CPLX, bool HALF>
+__global__ void __launch_bounds__(kEvalThreads)
+eloc_eval_tile_kernel(const u64 *__restrict__ bra, long long n, const double *__restrict__ h1e, const double *__restrict__ h2e,
+                      const u64 *__restrict__ key, const double *__restrict__ psi, long long N, GroupView gv,
+                      const HitRun *__restrict__ runs, const u32 *__restrict__ run_cnt, int run_stride, const u32 *__restrict__ hits,
+                      const u32 *__restrict__ self_pos, const double *__restrict__ hii, double *__restrict__ eloc,
+                      double *__restrict__ psi0_out, ExcGeom g) {
+  __shared__ OrbLists s_lists[kEvalThreads / 32];
+  __shared__ EvalTileSmem s_tile[kEvalThreads / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  EvalTileSmem &T = s_tile[warp];
+  const long long s0 = ((long long)blockIdx.x * (kEvalThreads / 32) + warp) * 32;
+  if (s0 >= n) return;
+  const long long s = s0 + lane;
+  const bool valid = s < n;
+  // ---- this lane's sample ---------------------------------------------------------------------------------------------
+  Onv<L> x;
+#pragma unroll
+  for (int w = 0; w < L; ++w) x.w[w] = valid ? bra[s * L + w] : 0ull;
+  const int nruns = valid ? (int)run_cnt[s] : 0;
+  const HitRun *my_runs = runs + s * run_stride;
+  bool redo = false;
+  for (int r = 0; r < nruns; ++r) redo |= (my_runs[r].cnt & kOverflow) != 0;
+  Cplx p0 = {0.0, 0.0};
+  if (valid && !redo) {
+    const u32 sp = self_pos[s];
+    if (sp != kNoSelf) p0 = load_psi<CPLX>(psi, (long long)__ldg(gv.rows[0] + sp));
+  }
+#pragma unroll
+  for (int w = 0; w < L; ++w) T.x[lane][w] = x.w[w];
+  T.p0[lane][0] = p0.re;
+  T.p0[lane][1] = p0.im;
+  {
+    Cplx a0 = {0.0, 0.0};
+    if (valid && !redo) accumulate<CPLX>(a0, p0, p0, hii[s]);  // row 0: (psi0 / psi0) * H_xx
+    T.acc[lane][0] = a0.re;
+    T.acc[lane][1] = a0.im;
+  }
+  __syncwarp();
+  const int max_runs = __reduce_max_sync(0xffffffffu, redo ? 0 : nruns);
+  int lists_owner = -1;
+  for (int r = 0; r < max_runs; ++r) {
+    HitRun mine = {0u, 0u};
+    if (!redo && r < nruns) mine = my_runs[r];
+    u32 incl = mine.cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const u32 up = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += up;
+    }
+    const u32 total = __shfl_sync(0xffffffffu, incl, 31);
+    for (u32 e0 = 0; e0 < total; e0 += 32) {
+      const u32 e = e0 + (u32)lane;
+      int j = 0;  // the sample that holds hit e: the first one whose inclusive prefix exceeds e
+#pragma unroll
+      for (int step = 16; step > 0; step >>= 1) {
+        const u32 v = __shfl_sync(0xffffffffu, incl, j + step - 1);
+        if (v <= e) j += step;
+      }
+      j = min(j, 31);
+      const u32 j_incl = __shfl_sync(0xffffffffu, incl, j), j_cnt = __shfl_sync(0xffffffffu, mine.cnt, j);
+      const u32 j_off = __shfl_sync(0xffffffffu, mine.off, j);
+      Onv<L> xs, y;
+#pragma unroll
+      for (int w = 0; w < L; ++w) xs.w[w] = T.x[j][w];
+      y = xs;
+      long long id = 0;
+      int kind = 0;  // 1 single, 2 double, 0 nothing to add
+      if (e < total) {
+        const u32 h = hits[j_off + (e - (j_incl - j_cnt))];
+        const bool grouping = (h & kHitA) != 0u;
+        const u32 pos = HALF ? (h & kHitPos) : (h & ~kHitA);
+        y = load_onv<L>((grouping ? gv.keys[1] : gv.keys[0]) + (size_t)pos * L);
+        bool ok = true;
+        if (HALF) {  // the scan tested one folded string only: class of the full key vs the scan it came from
+          const u64 d = y.w[0] ^ xs.w[0];
+          const int na = __popcll(d & kEven), nb = __popcll(d & kOdd);
+          const int moved = grouping ? nb : na, fixed = grouping ? na : nb;
+          const bool ok_own = (fixed == 0) & ((moved == 2) | (moved == 4));
+          const bool ok_ab = (na == 2) & (nb == 2);
+          ok = (h & kHitOwn) ? ok_own : ok_ab;
+        }
+        if (ok) {
+          kind = excitation_class<L>(xs, y);
+          id = (long long)__ldg((grouping ? gv.rows[1] : gv.rows[0]) + pos);
+        }
+      }
+      Cplx v = {0.0, 0.0};
+      const Cplx pj = {T.p0[j][0], T.p0[j][1]};
+      if (kind == 2) accumulate<CPLX>(v, load_psi<CPLX>(psi, id), pj, double_element<L, double>(xs, y, h2e));
+      // single excitations (rare): one at a time by the whole warp, terms gathered in parallel
+      u32 pend = __ballot_sync(0xffffffffu, kind == 1);
+      while (pend) {
+        const int src = __ffs(pend) - 1;
+        pend &= pend - 1u;
+        const int js = __shfl_sync(0xffffffffu, j, src);
+        Onv<L> xb, yb;
+#pragma unroll
+        for (int w = 0; w < L; ++w) {
+          xb.w[w] = T.x[js][w];
+          yb.w[w] = __shfl_sync(0xffffffffu, y.w[w], src);
+        }
+        if (lists_owner != js) {
+          __syncwarp();
+          build_lists<L>(xb, g.sorb, g.noA, g.noB, s_lists[warp], lane);
+          __syncwarp();
+          lists_owner = js;
+        }
+        const double hv = single_element_warp<L, double>(xb, yb, h1e, h2e, g.sorb, s_lists[warp].occ_order, s_lists[warp].n_occ);
+        if (lane == src) accumulate<CPLX>(v, load_psi<CPLX>(psi, id), pj, hv);
+      }
+      // sum of v over the lanes of the same sample (adjacent), then the last lane of every sample adds it in
+      const int jkey = e < total ? j : 32 + lane;  // idle lanes: segments of their own
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const double ur = __shfl_up_sync(0xffffffffu, v.re, o);
+        const double ui = CPLX ? __shfl_up_sync(0xffffffffu, v.im, o) : 0.0;
+        const int uj = __shfl_up_sync(0xffffffffu, jkey, o);
+        if (lane >= o && uj == jkey) {
+          v.re += ur;
+          if (CPLX) v.im += ui;
+        }
+      }
+      const int nextj = __shfl_down_sync(0xffffffffu, jkey, 1);
+      if (e < total && (lane == 31 || nextj != jkey)) {
+        T.acc[j][0] += v.re;
+        if (CPLX) T.acc[j][1] += v.im;
+      }
+      __syncwarp();
+    }
+  }
+  __syncwarp();
+  Cplx acc = {T.acc[lane][0], T.acc[lane][1]};
+  // ---- the reference's route for flagged samples: every excitation in row order, classic binary search ----------------------
+  u32 todo = __ballot_sync(0xffffffffu, valid && redo);
+  while (todo) {
+    const int src = __ffs(todo) - 1;
+    todo &= todo - 1u;
+    Onv<L> xb;
+#pragma unroll
+    for (int w = 0; w < L; ++w) xb.w[w] = T.x[src][w];
+    __syncwarp();
+    build_lists<L>(xb, g.sorb, g.noA, g.noB, s_lists[warp], lane);
+    __syncwarp();
+    lists_owner = src;
+    const OrbLists &lists = s_lists[warp];
+    Cplx q0 = {0.0, 0.0}, a = {0.0, 0.0};
+    const long long id0 = classic_search<L>(key, N, xb);
+    if (id0 >= 0) q0 = load_psi<CPLX>(psi, id0);
+    if (lane == 0) accumulate<CPLX>(a, q0, q0, hii[s0 + src]);
+    for (int r = lane; r < g.nsd; r += 32) {
+      const Exc ex = decode_exc(g, lists, r);
+      const long long id = classic_search<L>(key, N, apply_exc<L>(xb, ex));
+      if (id >= 0) accumulate<CPLX>(a, load_psi<CPLX>(psi, id), q0, exc_element<L, double>(xb, ex, h1e, h2e, g.sorb));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      a.re += __shfl_xor_sync(0xffffffffu, a.re, o);
+      if (CPLX) a.im += __shfl_xor_sync(0xffffffffu, a.im, o);
+    }
+    if (lane == src) {
+      acc = a;
+      p0 = q0;
+    }
+  }
+  if (valid) {
+    if (CPLX) {
+      eloc[2 * s] = acc.re;
+      eloc[2 * s + 1] = acc.im;
+      psi0_out[2 * s] = p0.re;
+      psi0_out[2 * s + 1] = p0.im;
+    } else {
+      eloc[s] = acc.re;
+      psi0_out[s] = p0.re;
+    }
+  }
+}
+
 // ---- host side --------------------------------------------------------------------------------------------
 // splits: CTAs per sample -- more than one only when there are too few samples to fill the GPU
 static int scan_threads(int n_groups) {
@@ -879,9 +1071,17 @@ static int launch_eloc_LC(const u64 *bra, long long n, const double *h1e, const 
                                              splits, ids, g, sm);
     count_launch();
     if (int rc = check_launch("eloc_scan_kernel")) return rc;
-    const unsigned eb = (unsigned)((nb + kEvalThreads / 32 - 1) / (kEvalThreads / 32));
-    eloc_eval_kernel<L, CPLX, HALF><<<eb, kEvalThreads, 0, st>>>(bra + b0 * L, nb, h1e, h2e, key, psi, N, gv, runs, run_cnt, lay.run_stride,
-                                                                 hits, self_pos, hii + b0, eloc + b0 * w, psi0 + b0 * w, g);
+    // 32 samples per warp; calls too small to fill the GPU that way keep one warp per sample
+    if ((nb >= 148LL * 32 * 8 && eloc_tuning().eval_tiles) || eloc_tuning().eval_tiles == 2) {
+      const unsigned eb = (unsigned)((nb + kEvalThreads - 1) / kEvalThreads);
+      eloc_eval_tile_kernel<L, CPLX, HALF><<<eb, kEvalThreads, 0, st>>>(bra + b0 * L, nb, h1e, h2e, key, psi, N, gv, runs, run_cnt,
+                                                                        lay.run_stride, hits, self_pos, hii + b0, eloc + b0 * w,
+                                                                        psi0 + b0 * w, g);
+    } else {
+      const unsigned eb = (unsigned)((nb + kEvalThreads / 32 - 1) / (kEvalThreads / 32));
+      eloc_eval_kernel<L, CPLX, HALF><<<eb, kEvalThreads, 0, st>>>(bra + b0 * L, nb, h1e, h2e, key, psi, N, gv, runs, run_cnt, lay.run_stride,
+                                                                   hits, self_pos, hii + b0, eloc + b0 * w, psi0 + b0 * w, g);
+    }
     count_launch();
     if (int rc = check_launch("eloc_eval_kernel")) return rc;
   }
