@@ -441,7 +441,7 @@ def run_ours(args):
         out["d_keys"], out["d_psi"] = d_keys, d_psi
         return out
 
-    keys_np = make_table("uniform", args.samples)
+    keys_np = make_table(args.table, args.samples)
     psi_np = make_psi(keys_np.shape[0], False)
     sampler = ClockSampler(local)
     if rank == 0:
@@ -486,7 +486,7 @@ def run_ours(args):
         if world > 1:
             dist.destroy_process_group()
         return
-    cfg = base_config(n_total, integrals)
+    cfg = base_config(n_total, integrals, args.table)
     cfg.update({"method": "sample-space, one-pass kernels", "l2": "flushed between timed steps (512 MiB write)",
                 "collectives": peer.route() if world > 1 else "none (one rank)",
                 "launch": "one CUDA graph per step (captured after the warm-up steps)" if main["graph"] else "kernel by kernel: " + main["why_eager"],
@@ -627,6 +627,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-api-path", action="store_true")
     ap.add_argument("--no-variants", action="store_true")
+    ap.add_argument("--table", default="uniform", help="sample set of the main measurement: uniform (the headline) or zipf0.8")
     ap.add_argument("--no-graph", action="store_true", help="launch the step kernel by kernel instead of replaying its CUDA graph")
     ap.add_argument("--no-peer", action="store_true", help="NCCL collectives only (no NVLink peer-memory pull kernels)")
     args = ap.parse_args()

@@ -25,7 +25,9 @@ struct ElocCounters {
   u32 slot_front;    // block route: samples placed in tiles
   u32 n_single;      // samples left to the per-sample kernel (stored at the back of the slot array)
   u32 single_next;
-  u32 pad[58];
+  u32 n_heavy;       // evaluation: samples with long hit lists, handed from the tile kernel to the warp-per-sample kernel
+  u32 heavy_next;    // ... and taken so far
+  u32 pad[56];
 };
 static_assert(sizeof(ElocCounters) == 256, "counters are 256 bytes");
 

@@ -634,11 +634,23 @@ eloc_eval_kernel(const u64 *__restrict__ bra, long long n, const double *__restr
                  const u64 *__restrict__ key, const double *__restrict__ psi, long long N, GroupView gv,
                  const HitRun *__restrict__ runs, const u32 *__restrict__ run_cnt, int run_stride, const u32 *__restrict__ hits,
                  const u32 *__restrict__ self_pos, const double *__restrict__ hii, double *__restrict__ eloc,
-                 double *__restrict__ psi0_out, ExcGeom g) {
+                 double *__restrict__ psi0_out, const u32 *__restrict__ list, ElocCounters *ctr, ExcGeom g) {
   __shared__ OrbLists s_lists[kEvalThreads / 32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const long long s = (long long)blockIdx.x * (kEvalThreads / 32) + warp;
-  if (s >= n) return;
+  // work items: every sample of the call (one per warp), or (list != nullptr) the samples the tile kernel put on the list of
+  // long hit lists, handed out one by one (their lengths differ by orders of magnitude)
+  const long long items = list != nullptr ? (long long)ctr->n_heavy : n;
+  for (;;) {
+  long long item;
+  if (list != nullptr) {
+    u32 t = 0;
+    if (lane == 0) t = atomicAdd(&ctr->heavy_next, 1u);
+    item = (long long)__shfl_sync(0xffffffffu, t, 0);
+  } else {
+    item = (long long)blockIdx.x * (kEvalThreads / 32) + warp;
+  }
+  if (item >= items) break;
+  const long long s = list != nullptr ? (long long)list[item] : item;
   const Onv<L> x = load_onv<L>(bra + s * L);
   const int nruns = (int)run_cnt[s];
   const HitRun *my_runs = runs + s * run_stride;
@@ -748,6 +760,9 @@ eloc_eval_kernel(const u64 *__restrict__ bra, long long n, const double *__restr
       psi0_out[s] = p0.re;
     }
   }
+  __syncwarp();  // the next item reuses this warp's orbital lists
+  if (list == nullptr) break;
+  }
 }
 
 // ---- evaluation, 32 samples per warp -------------------------------------------------------------------------------------
@@ -758,6 +773,11 @@ eloc_eval_kernel(const u64 *__restrict__ bra, long long n, const double *__restr
 // sample are adjacent) and the segment tails add into the sample's accumulator in shared memory -- a fixed order, no atomics.
 // Runs: round r of the outer loop takes run r of every sample of the tile (one or two rounds after the block kernel).
 // Samples flagged for the reference's route (overflow, duplicate keys) are then handled one by one by the whole warp.
+// Samples with long hit lists (a skewed table: thousands of hits for the samples of a heavy string, which sit next to each
+// other) would make one warp the tail of the launch: they are put on a list instead and the warp-per-sample kernel above
+// takes them, one warp each.
+constexpr u32 kHeavyHits = 256;
+
 struct EvalTileSmem {
   u64 x[32][kMaxL];
   double p0[32][2];
@@ -770,7 +790,7 @@ eloc_eval_tile_kernel(const u64 *__restrict__ bra, long long n, const double *__
                       const u64 *__restrict__ key, const double *__restrict__ psi, long long N, GroupView gv,
                       const HitRun *__restrict__ runs, const u32 *__restrict__ run_cnt, int run_stride, const u32 *__restrict__ hits,
                       const u32 *__restrict__ self_pos, const double *__restrict__ hii, double *__restrict__ eloc,
-                      double *__restrict__ psi0_out, ExcGeom g) {
+                      double *__restrict__ psi0_out, u32 *__restrict__ heavy_list, ElocCounters *ctr, ExcGeom g) {
   __shared__ OrbLists s_lists[kEvalThreads / 32];
   __shared__ EvalTileSmem s_tile[kEvalThreads / 32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -786,9 +806,18 @@ eloc_eval_tile_kernel(const u64 *__restrict__ bra, long long n, const double *__
   const int nruns = valid ? (int)run_cnt[s] : 0;
   const HitRun *my_runs = runs + s * run_stride;
   bool redo = false;
-  for (int r = 0; r < nruns; ++r) redo |= (my_runs[r].cnt & kOverflow) != 0;
+  u32 my_hits = 0;
+  for (int r = 0; r < nruns; ++r) {
+    const u32 c = my_runs[r].cnt;
+    redo |= (c & kOverflow) != 0;
+    my_hits += c & ~kOverflow;
+  }
+  // (the samples flagged for the reference's route go the same way: ~M binary searches each)
+  const bool heavy = valid && (redo || my_hits > kHeavyHits);
+  redo = false;
+  if (heavy) heavy_list[atomicAdd(&ctr->n_heavy, 1u)] = (u32)s;
   Cplx p0 = {0.0, 0.0};
-  if (valid && !redo) {
+  if (valid && !redo && !heavy) {
     const u32 sp = self_pos[s];
     if (sp != kNoSelf) p0 = load_psi<CPLX>(psi, (long long)__ldg(gv.rows[0] + sp));
   }
@@ -798,16 +827,16 @@ eloc_eval_tile_kernel(const u64 *__restrict__ bra, long long n, const double *__
   T.p0[lane][1] = p0.im;
   {
     Cplx a0 = {0.0, 0.0};
-    if (valid && !redo) accumulate<CPLX>(a0, p0, p0, hii[s]);  // row 0: (psi0 / psi0) * H_xx
+    if (valid && !redo && !heavy) accumulate<CPLX>(a0, p0, p0, hii[s]);  // row 0: (psi0 / psi0) * H_xx
     T.acc[lane][0] = a0.re;
     T.acc[lane][1] = a0.im;
   }
   __syncwarp();
-  const int max_runs = __reduce_max_sync(0xffffffffu, redo ? 0 : nruns);
+  const int max_runs = __reduce_max_sync(0xffffffffu, (redo || heavy) ? 0 : nruns);
   int lists_owner = -1;
   for (int r = 0; r < max_runs; ++r) {
     HitRun mine = {0u, 0u};
-    if (!redo && r < nruns) mine = my_runs[r];
+    if (!redo && !heavy && r < nruns) mine = my_runs[r];
     u32 incl = mine.cnt;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -929,7 +958,7 @@ eloc_eval_tile_kernel(const u64 *__restrict__ bra, long long n, const double *__
       p0 = q0;
     }
   }
-  if (valid) {
+  if (valid && !heavy) {
     if (CPLX) {
       eloc[2 * s] = acc.re;
       eloc[2 * s + 1] = acc.im;
@@ -965,7 +994,7 @@ int launch_eloc_block(const u64 *bra, long long n, const GroupView &gv, char *bl
                       int run_stride, u32 *hits, u32 *self_pos, u32 hit_cap, const ExcGeom &g, const u32 **slots_out, cudaStream_t st);
 
 struct ElocScratch {
-  long long hii, self_pos, run_cnt, runs, counters, block_ws, hits, total;
+  long long hii, self_pos, run_cnt, heavy, runs, counters, block_ws, hits, total;
   long long hit_cap, batch;
   int splits;      // same for every batch of the call (sized for the first, largest one)
   int warps;       // warps per scan CTA
@@ -985,11 +1014,11 @@ static ElocScratch eloc_scratch_layout(long long n, const ExcGeom &g, bool block
   l.warps = scan_threads(g.noB * g.nvB + 2) / 32;
   if (block) {
     // every sample of the call in one go (the samples of a beta string must stay together); hits per sample the
-    // buffer can take before samples fall back to the full route: 256 on average, at most 8 GiB in all
+    // buffer can take before samples fall back to the full route: 384 on average, at most 8 GiB in all
     l.batch = n < (1LL << 24) ? n : (1LL << 24);
     l.splits = 1;
     l.run_stride = block_run_stride() > l.warps ? block_run_stride() : l.warps;
-    l.hit_cap = l.batch * 256 + 65536;
+    l.hit_cap = l.batch * 384 + 65536;
   } else {
     // hits per sample the global buffer can take before samples fall back to the full route, and a
     // batch size that keeps the buffer at about 2 GiB
@@ -1008,7 +1037,8 @@ static ElocScratch eloc_scratch_layout(long long n, const ExcGeom &g, bool block
   l.hii = 0;
   l.self_pos = up(l.hii + 8 * n);
   l.run_cnt = up(l.self_pos + 4 * nb);
-  l.runs = up(l.run_cnt + 4 * nb);
+  l.heavy = up(l.run_cnt + 4 * nb);
+  l.runs = up(l.heavy + 4 * nb);
   l.counters = up(l.runs + (long long)sizeof(HitRun) * nb * l.run_stride);
   l.block_ws = l.counters + 256;
   l.hits = up(l.block_ws + (block ? block_scratch_bytes(nb) : 0));
@@ -1036,6 +1066,7 @@ static int launch_eloc_LC(const u64 *bra, long long n, const double *h1e, const 
   double *hii = reinterpret_cast<double *>(scratch + lay.hii);
   u32 *self_pos = reinterpret_cast<u32 *>(scratch + lay.self_pos);
   u32 *run_cnt = reinterpret_cast<u32 *>(scratch + lay.run_cnt);
+  u32 *heavy = reinterpret_cast<u32 *>(scratch + lay.heavy);
   HitRun *runs = reinterpret_cast<HitRun *>(scratch + lay.runs);
   ElocCounters *ctr = reinterpret_cast<ElocCounters *>(scratch + lay.counters);
   u32 *hits = reinterpret_cast<u32 *>(scratch + lay.hits);
@@ -1076,11 +1107,18 @@ static int launch_eloc_LC(const u64 *bra, long long n, const double *h1e, const 
       const unsigned eb = (unsigned)((nb + kEvalThreads - 1) / kEvalThreads);
       eloc_eval_tile_kernel<L, CPLX, HALF><<<eb, kEvalThreads, 0, st>>>(bra + b0 * L, nb, h1e, h2e, key, psi, N, gv, runs, run_cnt,
                                                                         lay.run_stride, hits, self_pos, hii + b0, eloc + b0 * w,
-                                                                        psi0 + b0 * w, g);
+                                                                        psi0 + b0 * w, heavy, ctr, g);
+      count_launch();
+      // the samples with long hit lists, one warp each (a fixed grid of persistent warps reads the list's length on the device)
+      const long long cap = 148LL * 12;
+      const long long want = (nb + kEvalThreads / 32 - 1) / (kEvalThreads / 32);
+      eloc_eval_kernel<L, CPLX, HALF><<<(unsigned)(want < cap ? want : cap), kEvalThreads, 0, st>>>(
+          bra + b0 * L, nb, h1e, h2e, key, psi, N, gv, runs, run_cnt, lay.run_stride, hits, self_pos, hii + b0, eloc + b0 * w, psi0 + b0 * w,
+          heavy, ctr, g);
     } else {
       const unsigned eb = (unsigned)((nb + kEvalThreads / 32 - 1) / (kEvalThreads / 32));
       eloc_eval_kernel<L, CPLX, HALF><<<eb, kEvalThreads, 0, st>>>(bra + b0 * L, nb, h1e, h2e, key, psi, N, gv, runs, run_cnt, lay.run_stride,
-                                                                   hits, self_pos, hii + b0, eloc + b0 * w, psi0 + b0 * w, g);
+                                                                   hits, self_pos, hii + b0, eloc + b0 * w, psi0 + b0 * w, nullptr, ctr, g);
     }
     count_launch();
     if (int rc = check_launch("eloc_eval_kernel")) return rc;
