@@ -120,12 +120,11 @@ struct TileCtx {
   u64 x;
   u32 a, sid, hit_cap;
   int run_stride;
-  LaneHits h;
 };
 
-// a lane's current block is full (or there is none yet): close it and take the next, twice as large
-__device__ __noinline__ void next_hit_block(TileCtx &c) {
-  LaneHits &h = c.h;
+// a lane's current block is full (or there is none yet): close it and take the next, twice as large.  The bookkeeping
+// travels by value so that it stays in registers on the caller's side (every emitted hit reads it).
+__device__ __noinline__ LaneHits next_hit_block(const TileCtx &c, LaneHits h) {
   if (h.cap) {
     c.my_runs[h.nrun] = HitRun{h.base, h.fill};
     ++h.nrun;
@@ -133,23 +132,23 @@ __device__ __noinline__ void next_hit_block(TileCtx &c) {
   const u32 ncap = h.cap ? 2u * h.cap : (u32)kFirstBlock;
   if (h.nrun == (u32)c.run_stride) {
     h.over = true;
-    return;
+    return h;
   }
   const u32 off = atomicAdd(&c.ctr->hit_cursor, ncap);
   if (off > c.hit_cap || ncap > c.hit_cap - off) {
     h.over = true;
-    return;
+    return h;
   }
   h.base = off;
   h.cap = ncap;
   h.fill = 0;
+  return h;
 }
 
-__device__ __forceinline__ void emit_hit(TileCtx &c, u32 v) {
-  LaneHits &h = c.h;
+__device__ __forceinline__ void emit_hit(const TileCtx &c, LaneHits &h, u32 v) {
   if (h.over) return;
   if (h.fill == h.cap) {
-    next_hit_block(c);
+    h = next_hit_block(c, h);
     if (h.over) return;
   }
   c.hits[h.base + h.fill++] = v;
@@ -164,7 +163,7 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // the queue holds blocks (8 staged keys) that contained a hit: look at each key again and emit the hits.  The lanes
 // stay together: entry i of every lane is examined at the same time, then the hits are emitted bit by bit
 template <bool OWN>
-__device__ __noinline__ void flush_blocks(TileCtx &c, u32 qn) {
+__device__ __noinline__ LaneHits flush_blocks(const TileCtx &c, u32 qn, LaneHits h) {
   BlockWarpSmem &S = *c.S;
   const int lane = threadIdx.x & 31;
   const u32 a = c.a;
@@ -194,10 +193,11 @@ __device__ __noinline__ void flush_blocks(TileCtx &c, u32 qn) {
       if (m) {
         const int u = __ffs(m) - 1;
         m &= m - 1u;
-        emit_hit(c, (gpos + (u32)u) | (OWN ? kHitOwn : 0u));
+        emit_hit(c, h, (gpos + (u32)u) | (OWN ? kHitOwn : 0u));
       }
     }
   }
+  return h;
 }
 
 // test the staged keys [0, cnt) (cnt a multiple of 16) against the lane's alpha string: 3 instructions per key
@@ -211,7 +211,7 @@ __device__ __forceinline__ bool one_pair(u32 a, u32 k) {
 }
 
 template <bool OWN, bool POW2>
-__device__ __forceinline__ void test_stage(TileCtx &c, BlockWarpSmem &S, u32 cnt, u32 a) {
+__device__ __forceinline__ void test_stage(const TileCtx &c, LaneHits &h, BlockWarpSmem &S, u32 cnt, u32 a) {
   const int lane = threadIdx.x & 31;
   const uint4 *st4 = reinterpret_cast<const uint4 *>(S.stage);
   char *qbase = reinterpret_cast<char *>(&S.queue[lane]);
@@ -244,19 +244,19 @@ __device__ __forceinline__ void test_stage(TileCtx &c, BlockWarpSmem &S, u32 cnt
       qoff += 64u;
     }
     if (__any_sync(0xffffffffu, qoff > 64u * (u32)(kQCap - 2))) {
-      flush_blocks<OWN>(c, qoff >> 6);
+      h = flush_blocks<OWN>(c, qoff >> 6, h);
       qoff = 0;
     }
   }
-  flush_blocks<OWN>(c, qoff >> 6);
+  h = flush_blocks<OWN>(c, qoff >> 6, h);
 }
 
 // Walk the groups [q_lo, q_hi) of the current beta string: S.goff[q_lo .. q_hi] holds the exclusive prefix of their
 // sizes in blocks of 8 keys.  Fill after fill: block descriptors (lanes over groups), copy (8 lanes per block, cp.async),
 // test.
 template <bool OWN>
-__device__ __forceinline__ void walk_groups(TileCtx &c, BlockWarpSmem &S, const BlockGeom &g, const u32 *__restrict__ halfB, int q_lo, int q_hi,
-                                            u32 a) {
+__device__ __forceinline__ void walk_groups(TileCtx &c, LaneHits &h, BlockWarpSmem &S, const BlockGeom &g, const u32 *__restrict__ halfB,
+                                            int q_lo, int q_hi, u32 a) {
   const int lane = threadIdx.x & 31;
   const u32 total = S.goff[q_hi];
   for (u32 fb = 0; fb < total; fb += (u32)(kStage / 8)) {
@@ -284,9 +284,9 @@ __device__ __forceinline__ void walk_groups(TileCtx &c, BlockWarpSmem &S, const 
     cp_async_wait_all();
     __syncwarp();
     c.a = a;
-    if (OWN) test_stage<true, false>(c, S, 8u * nblk2, a);
-    else if (g.pow2) test_stage<false, true>(c, S, 8u * nblk2, a);
-    else test_stage<false, false>(c, S, 8u * nblk2, a);
+    if (OWN) test_stage<true, false>(c, h, S, 8u * nblk2, a);
+    else if (g.pow2) test_stage<false, true>(c, h, S, 8u * nblk2, a);
+    else test_stage<false, false>(c, h, S, 8u * nblk2, a);
     __syncwarp();
   }
 }
@@ -325,7 +325,7 @@ eloc_block_kernel(const u64 *__restrict__ bra, const u32 *__restrict__ slots, co
     c.sid = sid;
     c.hit_cap = hit_cap;
     c.run_stride = run_stride;
-    c.h = LaneHits{0u, 0u, 0u, 0u, table_has_dup != 0u};
+    LaneHits h = {0u, 0u, 0u, 0u, table_has_dup != 0u};
     u32 remaining = table_has_dup ? 0u : __ballot_sync(0xffffffffu, active);
     // a tile holds the samples of one bucket of the grouping pass: normally one beta string, after a hash collision several
     while (remaining) {
@@ -361,7 +361,7 @@ eloc_block_kernel(const u64 *__restrict__ bra, const u32 *__restrict__ slots, co
         S.goff[sB + 1] = (r.y - r.x + 7u) >> 3;
       }
       __syncwarp();
-      walk_groups<true>(c, S, g, halfB, sB, sB + 1, a);
+      walk_groups<true>(c, h, S, g, halfB, sB, sB + 1, a);
       // two singles whose strings share a bucket: the folded test cannot tell them apart, so the bucket is walked for one
       // of them only.  Buckets are told apart by their first position; the set lives in the (now idle) stage buffer
       for (int i = lane; i < kDupSet; i += 32) S.stage[i] = 0xffffffffu;
@@ -403,9 +403,12 @@ eloc_block_kernel(const u64 *__restrict__ bra, const u32 *__restrict__ slots, co
         if (lane == 0) S.goff[sB] = running;
       }
       __syncwarp();
-      walk_groups<false>(c, S, g, halfB, 0, sB, a);
+      walk_groups<false>(c, h, S, g, halfB, 0, sB, a);
     }
-    // ---- every sample's own-alpha group (beta singles, beta-beta doubles): one key per lane, sample after sample ----------
+    // ---- every sample's own-alpha group (beta singles, beta-beta doubles): the group depends on the sample, so every lane
+    // walks ITS bucket of the alpha-grouped copy, four independent loads in flight (a lane reads consecutive words: its lines
+    // stay in L1; the 32 lanes touch 32 lines per load, which at ~3 loads per sample and key-chunk is nowhere near a limit).
+    // No shuffles, no serial dependence between samples.
     if (!table_has_dup) {
       uint2 rA = make_uint2(0u, 0u);
       if (active) {
@@ -414,31 +417,23 @@ eloc_block_kernel(const u64 *__restrict__ bra, const u32 *__restrict__ slots, co
         const u32 *stp = gv.start[1] + group_bucket<1>(y, 1, gv.shift);
         rA = make_uint2(__ldg(stp), __ldg(stp + 1));
       }
-      for (int j = 0; j < (int)tile.y; ++j) {
-        const u32 s0 = __shfl_sync(0xffffffffu, rA.x, j), e0 = __shfl_sync(0xffffffffu, rA.y, j);
-        const u32 fbj = __shfl_sync(0xffffffffu, fb, j);
-        for (u32 k0 = s0; k0 < e0; k0 += 32) {
-          const u32 p = k0 + (u32)lane;
-          u32 d = 31u;
-          if (p < e0) d = (u32)__popc(__ldg(halfA + p) ^ fbj);
-          const bool hit = d == 2u || d == 4u;
-          const u32 m = __ballot_sync(0xffffffffu, hit);
-          if (m) {
-            // the hits of this chunk go straight into sample j's block of the hit buffer (lane j owns the bookkeeping;
-            // a block holds at least 64 entries, so one fresh block always has room for a chunk)
-            const u32 cnt = (u32)__popc(m);
-            if (lane == j && !c.h.over && c.h.fill + cnt > c.h.cap) next_hit_block(c);
-            __syncwarp();
-            const u32 at = __shfl_sync(0xffffffffu, c.h.base + c.h.fill, j);
-            const bool over_j = __shfl_sync(0xffffffffu, (int)c.h.over, j) != 0;
-            if (hit && !over_j) hits[at + (u32)__popc(m & ((1u << lane) - 1u))] = p | kHitA | kHitOwn;
-            if (lane == j && !c.h.over) c.h.fill += cnt;
-          }
+      const u32 longest = __reduce_max_sync(0xffffffffu, rA.y - rA.x);
+      const u32 far = ~fb;  // at distance 32 from the lane's beta string
+      for (u32 i = 0; i < longest; i += 4) {
+        u32 k[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const u32 p = rA.x + i + (u32)u;
+          k[u] = p < rA.y ? __ldg(halfA + p) : far;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const u32 d = (u32)__popc(k[u] ^ fb);
+          if (d == 2u || d == 4u) emit_hit(c, h, (rA.x + i + (u32)u) | kHitA | kHitOwn);
         }
       }
     }
     if (active) {
-      LaneHits &h = c.h;
       if (h.over) {
         c.my_runs[0] = HitRun{0u, kOverflow};
         run_cnt[sid] = 1u;
