@@ -28,8 +28,14 @@
 namespace pynqs {
 
 constexpr int kBlkWarps = 4;     // warps per CTA; every warp works on its own tile
-constexpr int kStage = 1024;     // folded strings staged per warp and fill
-constexpr int kQCap = 48;        // queue entries per lane (16-bit: index of a block of 8 staged keys)
+#ifndef PYNQS_STAGE
+#define PYNQS_STAGE 512
+#endif
+#ifndef PYNQS_QCAP
+#define PYNQS_QCAP 32
+#endif
+constexpr int kStage = PYNQS_STAGE;  // folded strings staged per warp and fill
+constexpr int kQCap = PYNQS_QCAP;    // queue entries per lane (16-bit: index of a block of 8 staged keys)
 constexpr int kMaxGroups = 260;  // beta singles of a one-word ONV (<= 16 * 16) + the own group
 constexpr int kFirstBlock = 64;  // hit-buffer block sizes of a sample: 64, 128, ... (one HitRun each)
 
@@ -42,8 +48,8 @@ struct BlockWarpSmem {
   unsigned char blkcnt[kStage / 8];  // keys in the block (the rest is padding)
   unsigned char bpos[32];
 };
-constexpr int kDupSet = 512;  // open-addressing set of the bucket starts of a walk (lives in the stage buffer)
-static_assert(kDupSet <= kStage && kDupSet >= 2 * 256, "duplicate-bucket set: twice the largest number of groups");
+constexpr int kDupSet = 512;  // open-addressing set of the bucket starts of a walk (lives in the idle queue)
+static_assert(kDupSet * 4 <= kQCap * 32 * 2 && kDupSet >= 2 * 256, "duplicate-bucket set: twice the largest number of groups");
 
 __host__ __device__ inline u32 sample_log2_buckets(long long n) {
   u32 lg = 10;
@@ -276,10 +282,26 @@ __device__ __forceinline__ void walk_groups(TileCtx &c, LaneHits &h, BlockWarpSm
     __syncwarp();
     const u32 nblk2 = (nblk + 1u) & ~1u;  // the test loop takes 16 keys at a time
     const u32 sub = (u32)lane & 7u;
-    for (u32 b = (u32)lane >> 3; b < nblk2; b += 4) {
-      u32 *dst = &S.stage[8u * b + sub];
-      if (b < nblk && sub < (u32)S.blkcnt[b]) cp_async4(dst, halfB + S.blkpos[b] + sub);
-      else *dst = g.pad;
+    // 8 lanes per block, 4 blocks per pass, 4 passes in flight (the descriptors come out of shared memory: without the
+    // unrolling every pass would wait for its own two loads)
+    for (u32 b0 = (u32)lane >> 3; b0 < nblk2; b0 += 16) {
+      u32 cnt[4], pos[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const u32 b = b0 + 4u * (u32)u;
+        const bool in = b < nblk;
+        cnt[u] = in ? (u32)S.blkcnt[b] : 0u;
+        pos[u] = in ? S.blkpos[b] : 0u;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const u32 b = b0 + 4u * (u32)u;
+        if (b < nblk2) {
+          u32 *dst = &S.stage[8u * b + sub];
+          if (sub < cnt[u]) cp_async4(dst, halfB + pos[u] + sub);
+          else *dst = g.pad;
+        }
+      }
     }
     cp_async_wait_all();
     __syncwarp();
@@ -363,15 +385,16 @@ eloc_block_kernel(const u64 *__restrict__ bra, const u32 *__restrict__ slots, co
       __syncwarp();
       walk_groups<true>(c, h, S, g, halfB, sB, sB + 1, a);
       // two singles whose strings share a bucket: the folded test cannot tell them apart, so the bucket is walked for one
-      // of them only.  Buckets are told apart by their first position; the set lives in the (now idle) stage buffer
-      for (int i = lane; i < kDupSet; i += 32) S.stage[i] = 0xffffffffu;
+      // of them only.  Buckets are told apart by their first position; the set lives in the (now idle) hit queue
+      u32 *dupset = reinterpret_cast<u32 *>(S.queue);
+      for (int i = lane; i < kDupSet; i += 32) dupset[i] = 0xffffffffu;
       __syncwarp();
       for (int q = lane; q < sB; q += 32) {
         const uint2 r = S.rng[q];
         if (r.x == r.y) continue;
         u32 slot = (r.x * 0x9E3779B1u) >> (32 - 9);
         for (;;) {
-          const u32 old = atomicCAS(&S.stage[slot], 0xffffffffu, r.x);
+          const u32 old = atomicCAS(&dupset[slot], 0xffffffffu, r.x);
           if (old == 0xffffffffu) break;
           if (old == r.x) {
             S.rng[q] = make_uint2(0u, 0u);
@@ -507,7 +530,7 @@ int launch_eloc_block(const u64 *bra, long long n, const GroupView &gv, char *bl
   if (cudaFuncSetAttribute(eloc_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return check_launch("eloc_block_kernel smem opt-in");
   long long ctas = (n + 32 * kBlkWarps - 1) / (32 * kBlkWarps);
-  const long long cap = 148LL * 5;
+  const long long cap = 148LL * (long long)((227 * 1024) / (sizeof(BlockWarpSmem) * kBlkWarps + 1024));
   if (ctas > cap) ctas = cap;
   eloc_block_kernel<<<(unsigned)ctas, kBlkWarps * 32, smem, st>>>(bra, slots, tiles, ctr, gv, runs, run_cnt, run_stride, hits, self_pos, hit_cap, bg);
   count_launch();
