@@ -12,8 +12,8 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-fil
     $B --steps 2 --warmup 1 > gpurun_out/${TAG}_launches_bench.log 2>&1
 fi
 if [ "$WHAT" = eloc ] || [ "$WHAT" = all ]; then
-ncu --set full --clock-control none --import-source on -k 'regex:eloc_block_kernel|eloc_scan_kernel|eloc_eval_kernel' -s 3 -c 3 -f -o gpurun_out/${TAG}_eloc \
-    $B --steps 1 --warmup 1 --no-api-path > gpurun_out/${TAG}_eloc.log 2>&1
+ncu --set full --clock-control none --import-source on -k 'regex:eloc_block_kernel|eloc_eval_tile_kernel|diag_table_kernel|sample_alloc_kernel' -s 8 -c 4 -f -o gpurun_out/${TAG}_eloc \
+    $B --steps 1 --warmup 1 --no-api-path --no-graph > gpurun_out/${TAG}_eloc.log 2>&1
 fi
 if [ "$WHAT" = api ] || [ "$WHAT" = all ]; then
 ncu --set full --clock-control none --import-source on -k 'regex:enumerate_kernel|lut_indexed_kernel' -s 6 -c 2 -f -o gpurun_out/${TAG}_api \
