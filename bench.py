@@ -409,8 +409,8 @@ def run_ours(args):
         # the phases of the step, from eager launches with events in between (kernel by kernel, so launch-latency bound at
         # small per-rank sizes; the timed value above is the captured step)
         names = ["exchange", "table_sort_and_index", "eloc_kernels", "probabilities_and_statistics"]
-        acc, k_ms, nphase = [0.0] * 4, 0.0, 3
-        for _ in range(nphase):
+        acc, nphase = [0.0] * 4, 3
+        for it in range(nphase + 1):  # the first pass warms the eager allocations up again (the graph has a pool of its own)
             flush.fill_(1)
             torch.cuda.synchronize()
             if world > 1:
@@ -428,7 +428,7 @@ def run_ours(args):
             ev[4].record()
             torch.cuda.synchronize()
             for i in range(4):
-                acc[i] += ev[i].elapsed_time(ev[i + 1]) / nphase
+                acc[i] += ev[i].elapsed_time(ev[i + 1]) / nphase if it else 0.0
         out["phases"] = dict(zip(names, acc))
         out["kernel_ms"], out["kernel_samples"] = acc[2], hi - lo
         # E_loc of the whole sample set back in the ORIGINAL sample order (one rank only: parity legs).  The step returns the

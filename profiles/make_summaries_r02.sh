@@ -11,9 +11,12 @@ cp gpurun_out/${TAG}_launches.csv $OUT/launches.csv
   python profiles/launch_summary.py $OUT/launches.csv 2>/dev/null | head -45 ) > $OUT/launches_summary.txt
 python profiles/ncu_summary.py gpurun_out/${TAG}_eloc.ncu-rep > $OUT/eloc_kernels_ncu.txt
 python profiles/ncu_summary.py gpurun_out/${TAG}_api.ncu-rep > $OUT/api_kernels_ncu.txt
+python profiles/ncu_summary.py gpurun_out/${TAG}_lut.ncu-rep > $OUT/lut_kernel_ncu.txt
 ( echo "eloc_block_kernel: warp-instructions per sample and stall samples per phase (code between calls / exits)"
-  echo "python profiles/sass_phases.py gpurun_out/${TAG}_eloc.ncu-rep 1000000"
-  python profiles/sass_phases.py gpurun_out/${TAG}_eloc.ncu-rep 1000000 ) > $OUT/eloc_block_phases.txt
+  echo "python profiles/sass_phases.py gpurun_out/${TAG}_eloc.ncu-rep 1000000 --kernel=2"
+  python profiles/sass_phases.py gpurun_out/${TAG}_eloc.ncu-rep 1000000 --kernel=2
+  echo; echo "eloc_eval_tile_kernel:"
+  python profiles/sass_phases.py gpurun_out/${TAG}_eloc.ncu-rep 1000000 --kernel=3 ) > $OUT/eloc_block_phases.txt
 python - "$OUT" <<'PY'
 import json, re, sys
 out = sys.argv[1]
@@ -29,7 +32,7 @@ def grab(path):
             cur[m.group(1)] = v
     return ks
 e = grab(f"{out}/eloc_kernels_ncu.txt")
-a = grab(f"{out}/api_kernels_ncu.txt")
+a = grab(f"{out}/api_kernels_ncu.txt") + grab(f"{out}/lut_kernel_ncu.txt")
 dram = lambda k: int(k["dram__bytes_read.sum"] + k["dram__bytes_write.sum"])
 n = 1_000_000
 enum = next(k for k in a if "enumerate" in k["name"])

@@ -16,7 +16,9 @@ ncu --set full --clock-control none --import-source on -k 'regex:eloc_block_kern
     $B --steps 1 --warmup 1 --no-api-path --no-graph > gpurun_out/${TAG}_eloc.log 2>&1
 fi
 if [ "$WHAT" = api ] || [ "$WHAT" = all ]; then
-ncu --set full --clock-control none --import-source on -k 'regex:enumerate_kernel|lut_indexed_kernel' -s 6 -c 2 -f -o gpurun_out/${TAG}_api \
+ncu --set full --clock-control none --import-source on -k 'regex:enumerate_kernel' -s 4 -c 1 -f -o gpurun_out/${TAG}_api \
     $B --steps 1 --warmup 1 > gpurun_out/${TAG}_api.log 2>&1
+ncu --set full --clock-control none --import-source on -k 'regex:lut_indexed_kernel' -s 4 -c 1 -f -o gpurun_out/${TAG}_lut \
+    $B --steps 1 --warmup 1 > gpurun_out/${TAG}_lut.log 2>&1
 fi
 ls -la gpurun_out | tail -6

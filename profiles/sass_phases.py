@@ -1,20 +1,21 @@
 #!/usr/bin/env python
 """Instruction / stall-sample share of each phase of a kernel (phases = code between barriers, calls and exits),
-from an .ncu-rep captured with --import-source on:  python profiles/sass_phases.py rep [samples_per_launch] [lo hi]
+from an .ncu-rep captured with --import-source on:  python profiles/sass_phases.py rep [samples_per_launch] [lo hi] [--kernel=K]
 With lo hi: per-instruction listing (executions per sample) of SASS lines lo..hi."""
 import csv
 import subprocess
 import sys
 
 
-def main(path, per=1, lo=None, hi=None):
+def main(path, per=1, lo=None, hi=None, kernel=0):
     out = subprocess.run(["ncu", "-i", path, "--page", "source", "--csv"], capture_output=True, text=True).stdout.splitlines()
     rows = list(csv.reader(out))
-    hdr = next(r for r in rows if "Instructions Executed" in r)
-    hi_ = rows.index(hdr)
+    heads = [i for i, r in enumerate(rows) if "Instructions Executed" in r]  # one section per profiled launch
+    hi_ = heads[kernel]
+    hdr = rows[hi_]
     ie, src, smp = hdr.index("Instructions Executed"), hdr.index("Source"), hdr.index("# Samples")
     body = []
-    for r in rows[hi_ + 1:]:  # first kernel of the report only
+    for r in rows[hi_ + 1:]:  # this launch's section only
         if len(r) != len(hdr) or r == hdr:
             break
         body.append(r)
@@ -40,5 +41,6 @@ def main(path, per=1, lo=None, hi=None):
 
 
 if __name__ == "__main__":
-    a = sys.argv
-    main(a[1], float(a[2]) if len(a) > 2 else 1, int(a[3]) if len(a) > 4 else None, int(a[4]) if len(a) > 4 else None)
+    a = [x for x in sys.argv if not x.startswith("--kernel=")]
+    k = next((int(x.split("=")[1]) for x in sys.argv if x.startswith("--kernel=")), 0)  # --kernel=K: K-th launch of the report
+    main(a[1], float(a[2]) if len(a) > 2 else 1, int(a[3]) if len(a) > 4 else None, int(a[4]) if len(a) > 4 else None, k)
