@@ -59,11 +59,14 @@ template <int L>
 struct __align__(8) EnumEntry {
   u32 off, cmp;
 };
+#define PYNQS_WIDE_ENTRIES 1  // (8-byte entries + recomputed masks measured slower: 1.04 vs 0.89 ms)
+#ifdef PYNQS_WIDE_ENTRIES  // one-word ONVs: the excitation mask stored next to the HitInfo (16-byte entries, one LDS.128)
 template <>
 struct __align__(16) EnumEntry<1> {
   u64 mask;
   u32 off, cmp;
 };
+#endif
 
 template <int L>
 __device__ __forceinline__ EnumEntry<L> load_entry(const EnumEntry<L> *p) {
@@ -73,6 +76,7 @@ __device__ __forceinline__ EnumEntry<L> load_entry(const EnumEntry<L> *p) {
   e.cmp = v.y;
   return e;
 }
+#ifdef PYNQS_WIDE_ENTRIES
 template <>
 __device__ __forceinline__ EnumEntry<1> load_entry<1>(const EnumEntry<1> *p) {
   // one LDS.128 (the compiler splits a plain 16-byte shared load into two LDS.64, which doubles
@@ -86,13 +90,16 @@ __device__ __forceinline__ EnumEntry<1> load_entry<1>(const EnumEntry<1> *p) {
   e.cmp = v.w;
   return e;
 }
+#endif
 
 template <int L>
 __device__ __forceinline__ void set_mask(EnumEntry<L> &, u32, u32) {}
+#ifdef PYNQS_WIDE_ENTRIES
 template <>
 __device__ __forceinline__ void set_mask<1>(EnumEntry<1> &e, u32 a, u32 b) {
   e.mask = (1ull << a) | (1ull << b);
 }
+#endif
 
 template <int L>
 __device__ __forceinline__ Onv<L> entry_apply(const Onv<L> &x, const EnumEntry<L> &e) {
@@ -101,12 +108,14 @@ __device__ __forceinline__ Onv<L> entry_apply(const Onv<L> &x, const EnumEntry<L
   flip_bit<L>(y, (int)((e.cmp >> 16) & 0xffu));
   return y;
 }
+#ifdef PYNQS_WIDE_ENTRIES
 template <>
 __device__ __forceinline__ Onv<1> entry_apply<1>(const Onv<1> &x, const EnumEntry<1> &e) {
   Onv<1> y;
   y.w[0] = x.w[0] ^ e.mask;
   return y;
 }
+#endif
 
 template <int L>
 __device__ __forceinline__ void store_row_vec(u64 *dst, const Onv<L> &r) {
