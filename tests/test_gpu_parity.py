@@ -262,7 +262,14 @@ def test_eloc_full_space_and_rayleigh_quotient(scan_route):
     assert abs(e_dense - e_vmc) < 1e-10
 
 
-def test_eloc_sample_missing_from_table_gives_nan_like_reference():
+@pytest.mark.parametrize("route", ["default", "block"])
+def test_eloc_sample_missing_from_table_gives_nan_like_reference(route):
+    if route == "block":
+        from pynqs_b200 import _lib
+
+        _lib.set_tuning("block_min_samples", 1)
+        _lib.set_tuning("block_min_group", 4)
+        _lib.set_tuning("eval_tiles", 2)
     keys = S.random_onvs(300, 12, 3, 3, seed=80)
     h1e, h2e = S.random_packed_integrals(12, seed=81, symmetric=True)
     lut = WavefunctionLUT(dev(keys[:200]), dev(S.random_psi(200, seed=82)), 12, DEV, rank=0, world_size=1)
@@ -383,11 +390,18 @@ def test_eloc_tiny_tables_many_groups_per_bucket(nkeys, scan_route):
     np.testing.assert_allclose(e1.cpu().numpy(), want, rtol=1e-12, atol=0)
 
 
+@pytest.mark.parametrize("route", ["default", "block"])
 @pytest.mark.parametrize("sorb,noA,noB", [(40, 15, 15), (100, 3, 3)])
-def test_eloc_table_with_duplicate_keys_takes_the_reference_route(sorb, noA, noB):
+def test_eloc_table_with_duplicate_keys_takes_the_reference_route(sorb, noA, noB, route):
     """A table that holds some keys twice (the reference tolerates it: its binary search lands on one of the
     copies): the build notices, and every sample is evaluated by full enumeration + the reference's probe
     sequence, so even the choice among copies with DIFFERENT psi values is the reference's."""
+    if route == "block":  # grouping pass + block kernel + tile evaluation see the duplicate flag too
+        from pynqs_b200 import _lib
+
+        _lib.set_tuning("block_min_samples", 1)
+        _lib.set_tuning("block_min_group", 4)
+        _lib.set_tuning("eval_tiles", 2)
     seeds = S.random_onvs(3, sorb, noA, noB, seed=61)
     comb = O.comb(seeds, sorb, noA, noB).reshape(-1, seeds.shape[1])
     rng = np.random.default_rng(62)
@@ -839,3 +853,34 @@ def test_hij_2d_tiled_matrix_equals_untiled_rows_and_is_symmetric(L, sorb, na, n
     want = O.hij(keys[:4], keys[:m], h1e, h2e, sorb, 2 * na) if hasattr(O, "hij") else None
     if want is not None:
         np.testing.assert_array_equal(H[:4].cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+def test_block_route_product_table_every_tile_shape(cplx):
+    """Block kernel at its production settings on a table where the samples per beta string range from 1 to 150 (tiles of every
+    size, groups below the threshold left to the per-sample kernel, hit lists long enough for the warp-per-sample evaluator):
+    all samples against the three-call path, a subset against the oracle."""
+    sorb, noA, noB, nele = 40, 15, 15, 30
+    base = S.random_onvs(4000, sorb, noA, noB, seed=90).view(np.uint64).reshape(-1)
+    a_str = np.unique(base & np.uint64(0x5555555555555555))[:150]
+    b_str = np.unique(base & np.uint64(0xAAAAAAAAAAAAAAAA))[:120]
+    rng = np.random.default_rng(91)
+    rows = []
+    for i, b in enumerate(b_str):  # 1, 2, 3, ... up to 150 alpha strings on the i-th beta string
+        take = a_str[rng.permutation(a_str.size)[: 1 + (i * 5) % 150]]
+        rows.append(take | b)
+    keys = np.unique(np.concatenate(rows)).view(np.uint8).reshape(-1, 8)
+    assert keys.shape[0] >= 4096  # above block_min_samples: the default route is the block route
+    psi = S.random_psi(keys.shape[0], seed=92, complex_=cplx)
+    h1e, h2e = S.random_packed_integrals(sorb, seed=7, symmetric=True)
+    lut = WavefunctionLUT(dev(keys), dev(psi), sorb, DEV, rank=0, world_size=1)
+    x = lut.bra_key
+    e1, _, p1 = local_energy_sample_space(x, dev(h1e), dev(h2e), lut, sorb, nele, noA, noB, dtype=lut.dtype)
+    e3, _, p3 = local_energy_three_call(x, dev(h1e), dev(h2e), lut, sorb, nele, noA, noB, dtype=lut.dtype, batch=2048)
+    # (terms of order 1 that cancel to ~1e-5 for a few samples: the two routes add them in different orders)
+    np.testing.assert_allclose(e1.cpu().numpy(), e3.cpu().numpy(), rtol=1e-12, atol=1e-14)
+    assert torch.equal(torch.view_as_real(p1) if cplx else p1, torch.view_as_real(p3) if cplx else p3)
+    pick = np.arange(0, keys.shape[0], keys.shape[0] // 24)[:24]
+    skeys, spsi = lut.bra_key.cpu().numpy(), lut.wf_value.cpu().numpy()
+    want = O.eloc_sample_space(skeys[pick], h1e, h2e, skeys, spsi, sorb, nele, noA, noB)
+    np.testing.assert_allclose(e1.cpu().numpy()[pick], want, rtol=1e-12, atol=1e-14)
