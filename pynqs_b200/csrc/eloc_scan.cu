@@ -628,8 +628,10 @@ eloc_scan_kernel(const u64 *__restrict__ bra, long long n, GroupView gv, HitRun 
 }
 
 // ---- evaluation ---------------------------------------------------------------------------------------------
+// (launch bounds per variant: the 40-register budget that lets 12 CTAs of the real one-word kernel share an SM makes the
+//  complex and multi-word variants spill 250-390 bytes; they get 80 registers instead)
 template <int L, bool CPLX, bool HALF>
-__global__ void __launch_bounds__(kEvalThreads, 12)
+__global__ void __launch_bounds__(kEvalThreads, (CPLX || L > 1) ? 6 : 12)
 eloc_eval_kernel(const u64 *__restrict__ bra, long long n, const double *__restrict__ h1e, const double *__restrict__ h2e,
                  const u64 *__restrict__ key, const double *__restrict__ psi, long long N, GroupView gv,
                  const HitRun *__restrict__ runs, const u32 *__restrict__ run_cnt, int run_stride, const u32 *__restrict__ hits,
