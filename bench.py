@@ -495,7 +495,10 @@ def run_ours(args):
         "metric": METRIC, "value": main["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "config": cfg, "roofline": roof, "e2e": main["e2e"], "gpu_launches": main["launches"],
-        "phases_ms_rank0": main["phases"], "clocks": clocks,
+        "phases_ms_rank0": main["phases"],
+        "phases_note": "measured in extra EAGER steps with CUDA events between the phases (kernel by kernel, launch latency included); "
+                       "ms_per_step / value are the captured step",
+        "clocks": clocks,
         "energy": {"mean": main["stats"]["mean"], "var": main["stats"]["var"], "mean_e2e": main["mean_e2e"]},
     }
     ok = True
