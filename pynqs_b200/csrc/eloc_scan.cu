@@ -1064,7 +1064,7 @@ int launch_diag_f64(const u64 *bra, const double *h1e, const double *h2e, double
 template <int L, bool CPLX, bool HALF>
 static int launch_eloc_LC(const u64 *bra, long long n, const double *h1e, const double *h2e, const u64 *key, const double *psi,
                           long long N, const GroupView &gv, char *scratch, const ElocScratch &lay, double *eloc, double *psi0,
-                          const ExcGeom &g, cudaStream_t st) {
+                          const ExcGeom &g, cudaStream_t st, SideLane *diag_lane) {
   double *hii = reinterpret_cast<double *>(scratch + lay.hii);
   u32 *self_pos = reinterpret_cast<u32 *>(scratch + lay.self_pos);
   u32 *run_cnt = reinterpret_cast<u32 *>(scratch + lay.run_cnt);
@@ -1104,6 +1104,10 @@ static int launch_eloc_LC(const u64 *bra, long long n, const double *h1e, const 
                                              splits, ids, g, sm);
     count_launch();
     if (int rc = check_launch("eloc_scan_kernel")) return rc;
+    if (diag_lane != nullptr) {  // the diagonal elements (side stream) must be there now
+      if (!side_join(diag_lane, st)) return check_launch("eloc: join of the diagonal kernel");
+      diag_lane = nullptr;
+    }
     // 32 samples per warp; calls too small to fill the GPU that way keep one warp per sample
     if ((nb >= 148LL * 32 * 8 && eloc_tuning().eval_tiles) || eloc_tuning().eval_tiles == 2) {
       const unsigned eb = (unsigned)((nb + kEvalThreads - 1) / kEvalThreads);
@@ -1141,15 +1145,21 @@ int launch_eloc(const u64 *bra, long long n, const double *h1e, const double *h2
     return 4;
   }
   char *sc = static_cast<char *>(scratch);
-  if (int rc = launch_diag_f64(bra, h1e, h2e, reinterpret_cast<double *>(sc + lay.hii), n, 1, g.L, g.sorb, g.nele, st)) return rc;
+  // the diagonal <x|H|x> needs neither the table nor the hits: it runs on a side stream next to the scan kernels (which
+  // leave more than half of the warp slots free) and is joined before the evaluation
+  SideLane *side = side_lane(1);
+  const bool forked = side_fork(side, st);
+  if (int rc = launch_diag_f64(bra, h1e, h2e, reinterpret_cast<double *>(sc + lay.hii), n, 1, g.L, g.sorb, g.nele, forked ? side->stream : st))
+    return rc;
   const GroupView gv = group_view(group_ws, N, g.L);
+  SideLane *join = forked ? side : nullptr;  // joined before the first evaluation kernel
 #define PYNQS_ELOC_CASE(LL)                                                                                                  \
   case LL:                                                                                                                   \
-    return cplx ? launch_eloc_LC<LL, true, false>(bra, n, h1e, h2e, key, psi, N, gv, sc, lay, eloc, psi0, g, st)             \
-                : launch_eloc_LC<LL, false, false>(bra, n, h1e, h2e, key, psi, N, gv, sc, lay, eloc, psi0, g, st);
+    return cplx ? launch_eloc_LC<LL, true, false>(bra, n, h1e, h2e, key, psi, N, gv, sc, lay, eloc, psi0, g, st, join)       \
+                : launch_eloc_LC<LL, false, false>(bra, n, h1e, h2e, key, psi, N, gv, sc, lay, eloc, psi0, g, st, join);
   if (half) {
-    return cplx ? launch_eloc_LC<1, true, true>(bra, n, h1e, h2e, key, psi, N, gv, sc, lay, eloc, psi0, g, st)
-                : launch_eloc_LC<1, false, true>(bra, n, h1e, h2e, key, psi, N, gv, sc, lay, eloc, psi0, g, st);
+    return cplx ? launch_eloc_LC<1, true, true>(bra, n, h1e, h2e, key, psi, N, gv, sc, lay, eloc, psi0, g, st, join)
+                : launch_eloc_LC<1, false, true>(bra, n, h1e, h2e, key, psi, N, gv, sc, lay, eloc, psi0, g, st, join);
   }
   switch (g.L) {
     PYNQS_ELOC_CASE(1)

@@ -135,17 +135,14 @@ __global__ void __launch_bounds__(256) group_empty_kernel(GroupHeader *hdr, u32 
 
 // The two sorts are independent and far too small to fill the GPU (10^6 keys: ~16 us per pass): the second one
 // runs on a side stream, forked from and joined back into the caller's stream with events (capturable).
-struct SideLane {
-  cudaStream_t stream = nullptr;
-  cudaEvent_t fork = nullptr, join = nullptr;
-};
 static std::mutex g_side_mutex;
-static SideLane g_side[64];
+static SideLane g_side[2][64];
 
-static SideLane *side_lane() {
+SideLane *side_lane(int which) {
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-  SideLane &s = g_side[dev];
+  std::lock_guard<std::mutex> lock(g_side_mutex);
+  SideLane &s = g_side[which & 1][dev];
   if (s.stream == nullptr) {
     if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) != cudaSuccess ||
@@ -156,6 +153,16 @@ static SideLane *side_lane() {
     }
   }
   return &s;
+}
+
+bool side_fork(SideLane *s, cudaStream_t st) {
+  const bool ok = s != nullptr && cudaEventRecord(s->fork, st) == cudaSuccess && cudaStreamWaitEvent(s->stream, s->fork, 0) == cudaSuccess;
+  if (!ok) cudaGetLastError();
+  return ok;
+}
+
+bool side_join(SideLane *s, cudaStream_t st) {
+  return cudaEventRecord(s->join, s->stream) == cudaSuccess && cudaStreamWaitEvent(st, s->join, 0) == cudaSuccess;
 }
 
 int launch_group_build(const u64 *key, long long N, int L, void *ws, long long ws_bytes, cudaStream_t st) {
@@ -196,11 +203,8 @@ int launch_group_build(const u64 *key, long long N, int L, void *ws, long long w
     default: set_error("unsupported ONV length L=%d", L); return 1;
   }
   count_launch();
-  std::lock_guard<std::mutex> lock(g_side_mutex);
-  SideLane *side = side_lane();
-  const bool forked = side != nullptr && cudaEventRecord(side->fork, st) == cudaSuccess &&
-                      cudaStreamWaitEvent(side->stream, side->fork, 0) == cudaSuccess;
-  if (!forked) cudaGetLastError();
+  SideLane *side = side_lane(0);
+  const bool forked = side_fork(side, st);
   const long long cub_stride = (l.cub_bytes + 255) / 256 * 256;
   for (int g = 0; g < 2; ++g) {
     size_t tmp = l.cub_bytes;
@@ -213,8 +217,7 @@ int launch_group_build(const u64 *key, long long N, int L, void *ws, long long w
     }
     count_launch(((int)l.log2_buckets + 7) / 8 + 2);
   }
-  if (forked && (cudaEventRecord(side->join, side->stream) != cudaSuccess || cudaStreamWaitEvent(st, side->join, 0) != cudaSuccess))
-    return check_launch("group build join");
+  if (forked && !side_join(side, st)) return check_launch("group build join");
   const dim3 grid(blocks, 2);
 #define PYNQS_FINISH(LL)                                                                                                           \
   group_finish_kernel<LL><<<grid, 256, 0, st>>>(key, N, l.log2_buckets, bkt[0][1], bkt[1][1], rows[0], rows[1], keys[0], keys[1], \

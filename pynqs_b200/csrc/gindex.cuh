@@ -109,6 +109,17 @@ __device__ __forceinline__ u32 bucket_search(const u64 *__restrict__ keys, u32 l
 }
 
 // host side (gindex.cu)
+// A side stream per device with a pair of events: independent kernels of one call run next to the caller's stream
+// (fork: the side stream waits for what the caller's stream has queued; join: the caller's stream waits for the side
+// stream).  Capturable in a CUDA graph.  `which` selects one of two lanes (the table build and the local energy never share).
+struct SideLane {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+};
+SideLane *side_lane(int which);
+bool side_fork(SideLane *s, cudaStream_t st);
+bool side_join(SideLane *s, cudaStream_t st);
+
 GroupLayout group_layout(long long N, int L);
 GroupView group_view(const void *ws, long long N, int L);
 
