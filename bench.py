@@ -348,8 +348,6 @@ def run_ours(args):
         # every rank "samples" a contiguous piece of the unique set (disjoint pieces, like use_same_tree)
         cuts = [0] + split_length_idx(n_total, world)
         lo, hi = cuts[rank], cuts[rank + 1]
-        if n_total % world:
-            raise SystemExit("bench.py: --samples must be a multiple of the number of ranks")
         host_keys = torch.from_numpy(keys_np[lo:hi]).pin_memory()
         host_psi = torch.from_numpy(psi_np[lo:hi]).pin_memory()
         d_keys, d_psi = host_keys.to(dev), host_psi.to(dev)
@@ -417,7 +415,7 @@ def run_ours(args):
                 dist.barrier()
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
             ev[0].record()
-            uniq, wf, _ = exchange_unique_samples(d_keys, d_psi, None, disjoint=True, equal_sizes=True)
+            uniq, wf, _ = exchange_unique_samples(d_keys, d_psi, None, disjoint=True, sizes=step_obj.sizes)
             ev[1].record()
             lut = WavefunctionLUT(uniq, wf, SORB, dev, rank=rank, world_size=world)
             lut.group_index  # built here, inside the table phase

@@ -32,7 +32,7 @@ def _world() -> Tuple[int, int]:
 
 
 def exchange_unique_samples(onv: Tensor, psi: Tensor, counts: Optional[Tensor] = None, disjoint: bool = False,
-                            equal_sizes: bool = False) -> Tuple[Tensor, Tensor, Tensor]:
+                            equal_sizes: bool = False, sizes: Optional[list] = None) -> Tuple[Tensor, Tensor, Tensor]:
     """All ranks contribute their locally unique ONVs (uint8 [n_r, 8L]), psi values and sample
     counts; every rank returns the same merged (unique_onv, psi, counts).
 
@@ -40,7 +40,8 @@ def exchange_unique_samples(onv: Tensor, psi: Tensor, counts: Optional[Tensor] =
     concatenation in rank order, else torch.unique(dim=0) order (row-lexicographic, byte 0 most
     significant) with psi taken from the first occurrence and counts summed.
     `equal_sizes`: the caller guarantees every rank contributes the same number of rows, which saves
-    the all-gather of the counts and its host synchronisation."""
+    the all-gather of the counts and its host synchronisation; `sizes`: the caller knows every rank's row count (a list
+    of world_size ints) -- same saving for ragged pieces."""
     rank, world = _world()
     dev = onv.device
     n_r, w = onv.shape
@@ -48,7 +49,10 @@ def exchange_unique_samples(onv: Tensor, psi: Tensor, counts: Optional[Tensor] =
         all_onv, all_psi = onv, psi
         all_cnt = counts if counts is not None else torch.ones(n_r, dtype=torch.int64, device=dev)
     else:
-        if equal_sizes:
+        if sizes is not None:
+            n_list = [int(v) for v in sizes]
+            assert len(n_list) == world and n_list[rank] == n_r
+        elif equal_sizes:
             n_list = [n_r] * world
         else:
             n_all = torch.empty(world, dtype=torch.int64, device=dev)
@@ -78,7 +82,15 @@ def exchange_unique_samples(onv: Tensor, psi: Tensor, counts: Optional[Tensor] =
         all_cnt = outs[2] if counts is not None else torch.ones(all_onv.size(0), dtype=torch.int64, device=dev)
     if disjoint:
         return all_onv, all_psi, all_cnt
-    uniq, inv = torch.unique(all_onv, dim=0, return_inverse=True)
+    if all_onv.is_cuda:
+        # torch.unique(dim=0) orders rows with byte 0 most significant, i.e. as the little-endian integer of the byte-reversed
+        # row: the library's radix sort + unique on the reversed rows gives the same order without torch's comparison sort
+        from .C_extension import unique_onv
+
+        rev, inv = unique_onv(all_onv.flip(1).contiguous())
+        uniq = rev.flip(1).contiguous()
+    else:
+        uniq, inv = torch.unique(all_onv, dim=0, return_inverse=True)
     m = uniq.size(0)
     first = torch.full((m,), all_onv.size(0), dtype=torch.int64, device=dev)
     first.scatter_reduce_(0, inv, torch.arange(all_onv.size(0), device=dev), reduce="amin")

@@ -21,7 +21,8 @@ from .lut import WavefunctionLUT
 
 
 class SampleSpaceStep:
-    """Fixed-shape step: every rank contributes `n_local` unique ONVs (uint8 [n_local, 8L]) and their psi.
+    """Fixed-shape step: this rank contributes `n_local` unique ONVs (uint8 [n_local, 8L]) and their psi (the ranks' counts
+    may differ; the pieces must be disjoint, as with the sampler's use_same_tree).
 
         step = SampleSpaceStep(n_local, 8 * L, psi_dtype, h1e, h2e, sorb, nele, noa, nob)
         eloc, psi0, stats = step(onv, psi)          # tensors are views of static buffers, valid until the next call
@@ -38,6 +39,13 @@ class SampleSpaceStep:
         on = dist.is_available() and dist.is_initialized()
         self.rank = dist.get_rank() if on else 0
         self.world = dist.get_world_size() if on else 1
+        # every rank's sample count, exchanged once here so that the step itself needs no size handshake (and no host read)
+        self.sizes = [int(n_local)]
+        if self.world > 1:
+            mine = torch.tensor([int(n_local)], dtype=torch.int64, device=self.dev)
+            allv = torch.empty(self.world, dtype=torch.int64, device=self.dev)
+            dist.all_gather_into_tensor(allv, mine)
+            self.sizes = allv.tolist()
         self.onv = torch.zeros((n_local, width), dtype=torch.uint8, device=self.dev)
         self.psi = torch.zeros(n_local, dtype=psi_dtype, device=self.dev)
         self.graph: Optional[torch.cuda.CUDAGraph] = None
@@ -50,7 +58,7 @@ class SampleSpaceStep:
 
     def _body(self):
         sorb, nele, noa, nob = self.args
-        uniq, wf, _ = exchange_unique_samples(self.onv, self.psi, None, disjoint=True, equal_sizes=True)
+        uniq, wf, _ = exchange_unique_samples(self.onv, self.psi, None, disjoint=True, sizes=self.sizes)
         lut = WavefunctionLUT(uniq, wf, sorb, self.dev, rank=self.rank, world_size=self.world)
         eloc, psi0 = sample_space_energy_sharded(lut, self.h1e, self.h2e, sorb, nele, noa, nob)
         st = energy_statistics_amplitudes(eloc, psi0, lazy=True)

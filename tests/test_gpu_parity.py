@@ -884,3 +884,22 @@ def test_block_route_product_table_every_tile_shape(cplx):
     skeys, spsi = lut.bra_key.cpu().numpy(), lut.wf_value.cpu().numpy()
     want = O.eloc_sample_space(skeys[pick], h1e, h2e, skeys, spsi, sorb, nele, noA, noB)
     np.testing.assert_allclose(e1.cpu().numpy()[pick], want, rtol=1e-12, atol=1e-14)
+
+
+@pytest.mark.parametrize("L,sorb,na", [(1, 40, 15), (2, 100, 25), (3, 132, 3)])
+def test_non_disjoint_merge_on_the_device_equals_torch_unique(L, sorb, na):
+    """exchange_unique_samples(disjoint=False) on one rank: merged rows in torch.unique(dim=0) order (the reference's merge,
+    vmc/sample.py:672-690), psi of the first occurrence, counts summed -- through the library's sort instead of torch.unique."""
+    from pynqs_b200.distributed import exchange_unique_samples
+
+    base = S.random_onvs(3000, sorb, na, na, seed=95 + L)
+    rng = np.random.default_rng(96)
+    pick = rng.integers(0, base.shape[0], size=7000)
+    onv, psi = dev(base[pick]), dev(S.random_psi(7000, seed=97, complex_=True))
+    counts = dev(rng.integers(1, 9, size=7000).astype(np.int64))
+    uniq, wf, cnt = exchange_unique_samples(onv, psi, counts, disjoint=False)
+    want_u, want_inv = torch.unique(onv, dim=0, return_inverse=True)
+    assert torch.equal(uniq, want_u)
+    first = torch.full((want_u.size(0),), 7000, dtype=torch.int64, device=DEV).scatter_reduce_(0, want_inv, torch.arange(7000, device=DEV), reduce="amin")
+    assert torch.equal(torch.view_as_real(wf), torch.view_as_real(psi[first]))
+    assert torch.equal(cnt, torch.zeros(want_u.size(0), dtype=torch.int64, device=DEV).index_add_(0, want_inv, counts))

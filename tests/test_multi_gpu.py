@@ -33,6 +33,7 @@ def _worker(rank, world, port, n, cplx, q):
         from pynqs_b200 import synthetic as S
         from pynqs_b200.distributed import energy_statistics_amplitudes, exchange_unique_samples, sample_space_energy_sharded
         from pynqs_b200.lut import WavefunctionLUT, split_length_idx
+        from pynqs_b200.step import SampleSpaceStep
 
         _lib.set_tuning("block_min_samples", 1)
         sorb, noA, noB = 40, 15, 15
@@ -49,6 +50,13 @@ def _worker(rank, world, port, n, cplx, q):
         want, want0 = ops.eloc_sample_space(lut.bra_key[b:e].contiguous(), d(h1e), d(h2e), sorb, 30, noA, noB, lut.bra_key, lut.wf_value,
                                             lut.group_index)
         st = energy_statistics_amplitudes(eloc, psi0)
+        # the same through the captured step (ragged pieces: 20001 samples over two ranks), eager calls first, then replays
+        step = SampleSpaceStep(hi - lo, keys.shape[1], d(psi[:1]).dtype, d(h1e), d(h2e), sorb, 30, noA, noB, device=dev, warmup=1)
+        for _ in range(4):
+            e2, p2, st2 = step(d(keys[lo:hi]), d(psi[lo:hi]))
+        assert step.graph is not None, step.why_eager
+        assert torch.equal(torch.view_as_real(e2) if cplx else e2, torch.view_as_real(eloc) if cplx else eloc)
+        assert st2.result()["mean"] == st["mean"]
         torch.cuda.synchronize()
         q.put((rank, bool(torch.equal(torch.view_as_real(eloc) if cplx else eloc, torch.view_as_real(want) if cplx else want)),
                bool(torch.equal(torch.view_as_real(psi0) if cplx else psi0, torch.view_as_real(want0) if cplx else want0)), st["mean"], st["var"], e - b))
