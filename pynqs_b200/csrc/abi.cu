@@ -359,7 +359,8 @@ int pynqs_set_tuning(const char *name, int64_t value) {
   } knobs[] = {{"scan_threads", &t.scan_threads, 0, 256},        {"search_factor", &t.search_factor, 1, 4096},
                {"full_keys", &t.full_keys, 0, 1},                {"block_min_samples", &t.block_min_samples, 1, 1LL << 30},
                {"block_min_group", &t.block_min_group, 4, 32},   {"block_enable", &t.block_enable, 0, 1},
-               {"eval_tiles", &t.eval_tiles, 0, 2}};
+               {"eval_tiles", &t.eval_tiles, 0, 2},
+               {"lut_pipeline", &t.lut_pipeline, 0, 1}};
   if (name == nullptr) {
     t = ElocTuning();  // back to the production values
     return 0;

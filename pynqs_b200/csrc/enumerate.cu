@@ -157,20 +157,25 @@ __device__ __forceinline__ void class_rows(const Onv<L> &x, const EnumEntry<L> *
           // single h -> p: h1e(h,p) + sum over occupied k, in the reference's order, of <hk||pk>
           // SA packs hA | pA << 16, SB packs pB | hB << 16
           const u32 h = CLS == 0 ? (e1.cmp & 0xffu) : (e1.cmp >> 16), p = CLS == 0 ? (e1.cmp >> 16) : (e1.cmp & 0xffu);
+          // (32-bit element offsets: the table has sorb * 2 * na^2 <= 3.6e6 entries; the occupied orbitals are read four
+          //  at a time as one packed word of the order list; eight gathers in flight, added in order)
           const u32 na = (u32)prep.na;
-          const size_t kstride = (size_t)2 * na * na;
+          const u32 kstride = 2u * na * na;
           const int n_occ = lists.n_occ;
+          const u32 *occ4 = reinterpret_cast<const u32 *>(lists.occ_order);
           T v = (T)0.0;
           v += __ldg(h1e + (size_t)p * g.sorb + h);
-          const T *line = prep.s + ((size_t)(h & 1u) * na + (p >> 1)) * na + (h >> 1);
-          for (int q = 0; q < n_occ; q += 4) {
-            T t[4];
+          const u32 base = ((h & 1u) * na + (p >> 1)) * na + (h >> 1);
+          int q = 0;
+          for (; q + 8 <= n_occ; q += 8) {
+            const u32 w0 = occ4[q >> 2], w1 = occ4[(q >> 2) + 1];
+            T t[8];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) t[i] = (q + i < n_occ) ? __ldg(line + kstride * lists.occ_order[q + i]) : (T)0.0;
+            for (int i = 0; i < 8; ++i) t[i] = __ldg(prep.s + (base + kstride * (((i < 4 ? w0 : w1) >> (8 * (i & 3))) & 0xffu)));
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-              if (q + i < n_occ) v += t[i];
+            for (int i = 0; i < 8; ++i) v += t[i];
           }
+          for (; q < n_occ; ++q) v += __ldg(prep.s + (base + kstride * (u32)lists.occ_order[q]));
           val[j] = v;
           sgn[j] = e1.off;  // bit 31 = the single's sign
         }
@@ -209,8 +214,10 @@ template <int L, typename T, bool WITH_H, int CLS, int ROWS>
 __device__ __forceinline__ void enumerate_class(const Onv<L> &x, const EnumEntry<L> *__restrict__ tab, const TableOffsets &to,
                                                 const ExcGeom &g, const OrbLists &lists, const T *__restrict__ h1e,
                                                 const PrepView<T> &prep, u64 *__restrict__ comb_s, T *__restrict__ hmat_s,
-                                                int lo, int hi) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+                                                int lo, int hi, int first_warp = 0) {
+  // (first_warp: the warp that takes the first chunk -- the beta singles start where the alpha singles ended, so that the
+  //  two serial 31-term sums of a sample's singles run on different warps)
+  const int lane = threadIdx.x & 31, warp = ((threadIdx.x >> 5) - first_warp) & (kEnumThreads / 32 - 1);
   constexpr int kChunk = 32 * ROWS;
   for (int c = lo + warp * kChunk; c < hi; c += (kEnumThreads / 32) * kChunk) {
     Onv<L> row[ROWS];
@@ -264,7 +271,8 @@ enumerate_kernel(const u64 *__restrict__ bra, const T *__restrict__ h1e, PrepVie
   auto clip_lo = [&](int v) { return v > t_lo ? v : t_lo; };
   auto clip_hi = [&](int v) { return v < t_hi ? v : t_hi; };
   enumerate_class<L, T, WITH_H, 0, 1>(x, tab, to, g, lists, h1e, prep, comb_s, hmat_s, clip_lo(1), clip_hi(g.d0 + 1));
-  enumerate_class<L, T, WITH_H, 1, 1>(x, tab, to, g, lists, h1e, prep, comb_s, hmat_s, clip_lo(g.d0 + 1), clip_hi(g.d1 + 1));
+  enumerate_class<L, T, WITH_H, 1, 1>(x, tab, to, g, lists, h1e, prep, comb_s, hmat_s, clip_lo(g.d0 + 1), clip_hi(g.d1 + 1),
+                                      ((g.d0 + 31) >> 5) & (kEnumThreads / 32 - 1));
   enumerate_class<L, T, WITH_H, 2, kRowsPerThread>(x, tab, to, g, lists, h1e, prep, comb_s, hmat_s, clip_lo(g.d1 + 1), clip_hi(g.d2 + 1));
   enumerate_class<L, T, WITH_H, 3, kRowsPerThread>(x, tab, to, g, lists, h1e, prep, comb_s, hmat_s, clip_lo(g.d2 + 1), clip_hi(g.d3 + 1));
   enumerate_class<L, T, WITH_H, 4, kRowsPerThread>(x, tab, to, g, lists, h1e, prep, comb_s, hmat_s, clip_lo(g.d3 + 1), clip_hi((int)M));

@@ -9,6 +9,7 @@
 //              average) from the shared pool with one atomicAdd;
 //   3. fill  : every key inserts (tag, row) into its two regions (32-bit CAS, linear probing
 //              inside the region).
+#include "eloc.cuh"
 #include "lut.cuh"
 
 namespace pynqs {
@@ -38,6 +39,120 @@ lut_indexed_kernel(const u64 *__restrict__ key, long long N, IndexView iv, const
     const long long r = dup ? classic_search<L>(key, N, x) : indexed_search<L>(key, iv, x);
     __stcs(idx + t, r);
     __stcs(mask + t, (unsigned char)(r >= 0));
+  }
+}
+
+// Four CONSECUTIVE queries per thread (one-word ONVs).  The queries of wavefunction_lut are the rows of comb[n, M]: long runs
+// of them share a beta string (alpha singles, alpha-alpha doubles, the 75-row blocks of alpha-beta doubles) or an alpha string
+// (beta singles, beta-beta doubles).  A thread therefore
+//   1. reads its 32 bytes of queries with two 16-byte loads (a warp reads 1 KB contiguous),
+//   2. finds the region of its queries with ONE directory probe when they share the beta string, or else the alpha string
+//      (then through the alpha-grouped directory; a thread that straddles the end of a run probes for every query),
+//   3. issues the four tag-bucket loads together, and only then
+//   4. looks at the tags (a match or an overflowed bucket goes through region_probe, which verifies against the key table),
+//   5. writes the four indices with two 16-byte stores and the four mask bytes with one 4-byte store.
+// The dependent chain per thread is query -> directory -> tags -> store for four queries instead of for each one, and the
+// hash + directory probe of the shared string is paid once.  Same answers as lut_indexed_kernel (both directories index
+// every key); tables with duplicate keys and unaligned tensors keep the one-query kernel.
+__global__ void __launch_bounds__(256)
+lut_batched_kernel(const u64 *__restrict__ key, long long N, IndexView iv, const u64 *__restrict__ q, long long n,
+                   long long *__restrict__ idx, unsigned char *__restrict__ mask) {
+  constexpr int Q = 4;
+  const u32 lg_dir = iv.log2_dir;
+  const long long groups = n / Q;
+  const bool dup = iv.hdr->has_dup != 0;  // duplicates: reproduce the reference's probe sequence instead
+  // the queries of the NEXT round are fetched before the current ones are worked on: the stream of queries comes out of
+  // DRAM, and a thread that waited for its own 32 bytes each round left the memory system idle (a quarter of all stall
+  // samples sat on the first use of the queries)
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  ulonglong2 n0 = make_ulonglong2(0ull, 0ull), n1 = n0;
+  if (g < groups) {
+    const ulonglong2 *src = reinterpret_cast<const ulonglong2 *>(q + Q * g);
+    n0 = __ldcs(src), n1 = __ldcs(src + 1);
+  }
+  for (; g < groups; g += stride) {
+    u64 x[Q];
+    x[0] = n0.x, x[1] = n0.y, x[2] = n1.x, x[3] = n1.y;
+    if (g + stride < groups) {
+      const ulonglong2 *src = reinterpret_cast<const ulonglong2 *>(q + Q * (g + stride));
+      n0 = __ldcs(src), n1 = __ldcs(src + 1);
+    }
+    long long r[Q];
+    if (dup) {
+#pragma unroll
+      for (int j = 0; j < Q; ++j) {
+        Onv<1> o;
+        o.w[0] = x[j];
+        r[j] = classic_search<1>(key, N, o);
+      }
+    } else {
+    // ---- regions ----------------------------------------------------------------------------------------------------
+    // One directory probe per thread when its four queries share the beta string, or else the alpha string (then through
+    // the alpha-grouped directory); threads that straddle the end of a run probe the beta directory for every query.
+    u64 desc[Q];
+    const u64 diff = (x[0] ^ x[1]) | (x[0] ^ x[2]) | (x[0] ^ x[3]);
+    const bool same_b = (diff & kOdd) == 0ull, same_a = (diff & kEven) == 0ull;
+    const bool by_alpha = !same_b && same_a;  // the whole thread goes through the alpha-grouped directory
+    {
+      Onv<1> o;
+      o.w[0] = x[0];
+      const u64 d0 = dir_find(by_alpha ? iv.dir[1] : iv.dir[0], lg_dir, hash_string<1>(o, by_alpha ? kEven : kOdd));
+#pragma unroll
+      for (int j = 0; j < Q; ++j) desc[j] = d0;
+      if (!same_b && !same_a) {
+        // the end of a run inside the thread's four queries (nearly every warp has such a thread: the runs are 75 rows
+        // long): ONE more probe, for the beta string of the last query, covers the queries of the second run; what
+        // matches neither (three runs in four queries: the seams between excitation classes) is probed one by one
+        o.w[0] = x[Q - 1];
+        const u64 d3 = dir_find(iv.dir[0], lg_dir, hash_beta<1>(o));
+        desc[Q - 1] = d3;
+#pragma unroll
+        for (int j = 1; j < Q - 1; ++j) {
+          if (((x[j] ^ x[Q - 1]) & kOdd) == 0ull) {
+            desc[j] = d3;
+          } else if (((x[j] ^ x[0]) & kOdd) != 0ull) {
+            o.w[0] = x[j];
+            desc[j] = dir_find(iv.dir[0], lg_dir, hash_beta<1>(o));
+          }
+        }
+      }
+    }
+    const u64 other = by_alpha ? kOdd : kEven;  // the string the region is hashed by
+    // ---- tag buckets: four loads in flight ----------------------------------------------------------------------------
+    uint4 t[Q];
+    u32 tag[Q];
+#pragma unroll
+    for (int j = 0; j < Q; ++j) {
+      Onv<1> o;
+      o.w[0] = x[j];
+      const u64 h2 = hash_string<1>(o, other);
+      tag[j] = hash_tag(h2);
+      t[j] = make_uint4(0u, 0u, 0u, 0u);
+      const u32 off = (u32)desc[j], lg = (u32)(desc[j] >> 32);
+      if ((int)lg >= 0) {  // (kNoRegion has all bits set; a real region has lg <= 31)
+        // top lg bits of the high hash word = h2 >> (64 - lg), and 0 for a one-bucket region, in one funnel shift
+        const u32 bkt = __funnelshift_l((u32)(h2 >> 32), 0u, lg);
+        t[j] = __ldg(iv.pool + off + bkt);
+      }
+    }
+    // ---- results ---------------------------------------------------------------------------------------------------------
+#pragma unroll
+    for (int j = 0; j < Q; ++j) {
+      r[j] = -1;
+      if (tags_match(t[j], tag[j]) || bucket_overflowed(t[j])) {  // rare: a hit, a tag collision or a full bucket
+        Onv<1> o;
+        o.w[0] = x[j];
+        const u64 h2 = hash_string<1>(o, other);
+        r[j] = region_probe<1>(key, iv, desc[j], h2, [&]() { return o; });
+      }
+    }
+    }
+    longlong2 *dst = reinterpret_cast<longlong2 *>(idx + Q * g);
+    __stcs(dst, make_longlong2(r[0], r[1]));
+    __stcs(dst + 1, make_longlong2(r[2], r[3]));
+    const u32 m4 = (u32)(r[0] >= 0) | ((u32)(r[1] >= 0) << 8) | ((u32)(r[2] >= 0) << 16) | ((u32)(r[3] >= 0) << 24);
+    __stcs(reinterpret_cast<unsigned int *>(mask + Q * g), m4);
   }
 }
 
@@ -218,9 +333,24 @@ int launch_lut_hashed(const u64 *key, long long N, const u64 *q, long long n, in
                       unsigned char *mask, cudaStream_t st) {
   if (n == 0) return 0;
   const IndexView iv = index_view(ws, N);
-  const unsigned blocks = grid_for(n, 256, 148LL * 64);
+  // one-word ONVs, 16-byte aligned tensors: four consecutive queries per thread; the (up to three) last queries and every
+  // other case go through the one-query kernel.  Both kernels fall back to the reference's probe sequence by themselves when
+  // the build found duplicate keys.
+  long long done = 0;
+  const bool aligned = (reinterpret_cast<uintptr_t>(q) & 15u) == 0 && (reinterpret_cast<uintptr_t>(idx) & 15u) == 0 &&
+                       (reinterpret_cast<uintptr_t>(mask) & 3u) == 0;
+  if (L == 1 && aligned && n >= 4 && eloc_tuning().lut_pipeline) {
+    const long long groups = n / 4;
+    lut_batched_kernel<<<grid_for(groups, 256, 148LL * 64), 256, 0, st>>>(key, N, iv, q, groups * 4, idx, mask);
+    count_launch();
+    if (int rc = check_launch("lut_batched_kernel")) return rc;
+    done = groups * 4;
+    if (done == n) return 0;
+  }
+  const long long rest = n - done;
+  const unsigned blocks = grid_for(rest, 256, 148LL * 64);
   switch (L) {
-    case 1: lut_indexed_kernel<1><<<blocks, 256, 0, st>>>(key, N, iv, q, n, idx, mask); break;
+    case 1: lut_indexed_kernel<1><<<blocks, 256, 0, st>>>(key, N, iv, q + done, rest, idx + done, mask + done); break;
     case 2: lut_indexed_kernel<2><<<blocks, 256, 0, st>>>(key, N, iv, q, n, idx, mask); break;
     case 3: lut_indexed_kernel<3><<<blocks, 256, 0, st>>>(key, N, iv, q, n, idx, mask); break;
     default: set_error("unsupported ONV length L=%d", L); return 1;
