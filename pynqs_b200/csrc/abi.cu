@@ -360,7 +360,7 @@ int pynqs_set_tuning(const char *name, int64_t value) {
                {"full_keys", &t.full_keys, 0, 1},                {"block_min_samples", &t.block_min_samples, 1, 1LL << 30},
                {"block_min_group", &t.block_min_group, 4, 32},   {"block_enable", &t.block_enable, 0, 1},
                {"eval_tiles", &t.eval_tiles, 0, 2},
-               {"lut_pipeline", &t.lut_pipeline, 0, 1}};
+               {"lut_pipeline", &t.lut_pipeline, 0, 1},          {"block_parts", &t.block_parts, 0, 4}};
   if (name == nullptr) {
     t = ElocTuning();  // back to the production values
     return 0;

@@ -40,6 +40,7 @@ struct ElocTuning {
   int block_min_group = 8;     // samples sharing a beta string needed for a tile of the block kernel
   int block_enable = 1;
   int eval_tiles = 1;          // 1: large calls evaluate 32 samples per warp; 2: every call does; 0: one warp per sample
+  int block_parts = 0;         // block kernel: parts a tile's alpha-beta groups are split into (0: by the number of tiles; 1, 2, 4)
   int lut_pipeline = 1;        // lut_indexed_kernel: next query and its directory slot fetched ahead (0: one query at a time)
 };
 ElocTuning &eloc_tuning();

@@ -49,7 +49,7 @@ struct BlockWarpSmem {
   unsigned char bpos[32];
 };
 constexpr int kDupSet = 512;  // open-addressing set of the bucket starts of a walk (lives in the idle queue)
-static_assert(kDupSet * 4 <= kQCap * 32 * 2 && kDupSet >= 2 * 256, "duplicate-bucket set: twice the largest number of groups");
+static_assert(kDupSet * 4 <= kQCap * 32 * 2 && kDupSet <= kStage && kDupSet >= 2 * 256, "duplicate-bucket set: twice the largest number of groups");
 
 __host__ __device__ inline u32 sample_log2_buckets(long long n) {
   u32 lg = 10;
@@ -113,6 +113,7 @@ struct BlockGeom {
 
 struct LaneHits {  // where a lane's sample keeps its hits in the global buffer
   u32 base, fill, cap, nrun;
+  u32 end;  // run records [.., end) of the sample belong to this part of the tile
   bool over;
 };
 
@@ -136,7 +137,7 @@ __device__ __noinline__ LaneHits next_hit_block(const TileCtx &c, LaneHits h) {
     ++h.nrun;
   }
   const u32 ncap = h.cap ? 2u * h.cap : (u32)kFirstBlock;
-  if (h.nrun == (u32)c.run_stride) {
+  if (h.nrun == h.end) {
     h.over = true;
     return h;
   }
@@ -313,16 +314,32 @@ __device__ __forceinline__ void walk_groups(TileCtx &c, LaneHits &h, BlockWarpSm
   }
 }
 
+// SPLIT: the alpha-beta groups of a tile are split over several warps (see `parts` below); a template parameter so that
+// the whole-tile kernel of large calls carries none of the bookkeeping.
+template <bool SPLIT>
 __global__ void __launch_bounds__(kBlkWarps * 32)
 eloc_block_kernel(const u64 *__restrict__ bra, const u32 *__restrict__ slots, const uint2 *__restrict__ tiles, ElocCounters *ctr, GroupView gv,
                   HitRun *__restrict__ runs, u32 *__restrict__ run_cnt, int run_stride, u32 *__restrict__ hits, u32 *__restrict__ self_pos,
-                  u32 hit_cap, BlockGeom g) {
+                  u32 hit_cap, BlockGeom g, u32 force_parts) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   BlockWarpSmem &S = reinterpret_cast<BlockWarpSmem *>(smem_raw)[warp];
   const u32 table_has_dup = __ldg(&gv.hdr->has_dup);
   const u32 ntiles = ctr->tile_count;  // final: written by the grouping pass, which finished before this kernel started
   const int sB = g.noB * g.nvB;
+  // Few tiles (a rank's share of the samples at 8 GPUs; the launcher decides by the number of samples): with ~1.2 tiles per
+  // resident warp the launch takes the time of two tiles.  The alpha-beta groups of a tile are then split into `parts` ranges that different warps walk (part 0 also takes
+  // the tile's own group and the samples' own-alpha groups); every part writes its hits to run records of its own
+  // (run_stride / parts each), so nothing is shared between the parts but the read-only table.  Every part repeats the
+  // tile's set-up (~12 % of a tile), so two parts is where it stops paying: measured for 125 000 samples 0.700 / 0.656 /
+  // 0.738 ms with 1 / 2 / 4 parts (profiles/micro/eloc_slice.py).
+  u32 parts = 1;
+  if (SPLIT) {
+    parts = force_parts ? force_parts : 2u;
+    if ((u32)run_stride < 2u * parts) parts = 1;
+  }
+  const u32 runs_per_part = (u32)run_stride / parts;
+  const u32 nitems = ntiles * parts;
   const u32 *__restrict__ halfB = gv.half[0];
   const u32 *__restrict__ halfA = gv.half[1];
   const u32 all_beta = fold_beta(g.sorb >= 64 ? ~0ull : ((1ull << g.sorb) - 1ull));
@@ -330,7 +347,9 @@ eloc_block_kernel(const u64 *__restrict__ bra, const u32 *__restrict__ slots, co
     u32 t = 0;
     if (lane == 0) t = atomicAdd(&ctr->tile_next, 1u);
     t = __shfl_sync(0xffffffffu, t, 0);
-    if (t >= ntiles) break;
+    if (t >= nitems) break;
+    const u32 part = t / ntiles;  // part-major: the (heavier) parts 0 are handed out first
+    t -= part * ntiles;
     const uint2 tile = tiles[t];
     const bool active = (u32)lane < tile.y;
     const u32 sid = active ? slots[tile.x + lane] : 0u;
@@ -347,7 +366,8 @@ eloc_block_kernel(const u64 *__restrict__ bra, const u32 *__restrict__ slots, co
     c.sid = sid;
     c.hit_cap = hit_cap;
     c.run_stride = run_stride;
-    LaneHits h = {0u, 0u, 0u, 0u, table_has_dup != 0u};
+    LaneHits h = {0u, 0u, 0u, part * runs_per_part, (part + 1u) * runs_per_part, table_has_dup != 0u};
+    const int q_part_lo = (int)((u32)sB * part / parts), q_part_hi = (int)((u32)sB * (part + 1u) / parts);
     u32 remaining = table_has_dup ? 0u : __ballot_sync(0xffffffffu, active);
     // a tile holds the samples of one bucket of the grouping pass: normally one beta string, after a hash collision several
     while (remaining) {
@@ -383,11 +403,17 @@ eloc_block_kernel(const u64 *__restrict__ bra, const u32 *__restrict__ slots, co
         S.goff[sB + 1] = (r.y - r.x + 7u) >> 3;
       }
       __syncwarp();
-      walk_groups<true>(c, h, S, g, halfB, sB, sB + 1, a);
+      if (part == 0u) walk_groups<true>(c, h, S, g, halfB, sB, sB + 1, a);
       // two singles whose strings share a bucket: the folded test cannot tell them apart, so the bucket is walked for one
-      // of them only.  Buckets are told apart by their first position; the set lives in the (now idle) hit queue
+      // of them only -- the one with the SMALLEST group number, so that every part of a split tile drops the same ones.
+      // Buckets are told apart by their first position; the set lives in the (now idle) hit queue, the smallest group number
+      // of every bucket in the (now idle) stage buffer, a group's slot of the set in goff (recomputed below)
       u32 *dupset = reinterpret_cast<u32 *>(S.queue);
-      for (int i = lane; i < kDupSet; i += 32) dupset[i] = 0xffffffffu;
+      u32 *minq = S.stage;
+      for (int i = lane; i < kDupSet; i += 32) {
+        dupset[i] = 0xffffffffu;
+        minq[i] = 0xffffffffu;
+      }
       __syncwarp();
       for (int q = lane; q < sB; q += 32) {
         const uint2 r = S.rng[q];
@@ -395,13 +421,16 @@ eloc_block_kernel(const u64 *__restrict__ bra, const u32 *__restrict__ slots, co
         u32 slot = (r.x * 0x9E3779B1u) >> (32 - 9);
         for (;;) {
           const u32 old = atomicCAS(&dupset[slot], 0xffffffffu, r.x);
-          if (old == 0xffffffffu) break;
-          if (old == r.x) {
-            S.rng[q] = make_uint2(0u, 0u);
-            break;
-          }
+          if (old == 0xffffffffu || old == r.x) break;
           slot = (slot + 1u) & (u32)(kDupSet - 1);
         }
+        atomicMin(&minq[slot], (u32)q);
+        S.goff[q] = slot;
+      }
+      __syncwarp();
+      for (int q = lane; q < sB; q += 32) {
+        const uint2 r = S.rng[q];
+        if (r.x != r.y && minq[S.goff[q]] != (u32)q) S.rng[q] = make_uint2(0u, 0u);
       }
       __syncwarp();
       // first block of every group: exclusive prefix over the groups' sizes in blocks of 8
@@ -410,7 +439,7 @@ eloc_block_kernel(const u64 *__restrict__ bra, const u32 *__restrict__ slots, co
         for (int q0 = 0; q0 < sB; q0 += 32) {
           const int q = q0 + lane;
           u32 nb = 0;
-          if (q < sB) {
+          if (q >= q_part_lo && q < q_part_hi) {  // (the buckets of the other parts' groups count as empty here)
             const uint2 r = S.rng[q];
             nb = (r.y - r.x + 7u) >> 3;
           }
@@ -432,7 +461,7 @@ eloc_block_kernel(const u64 *__restrict__ bra, const u32 *__restrict__ slots, co
     // walks ITS bucket of the alpha-grouped copy, four independent loads in flight (a lane reads consecutive words: its lines
     // stay in L1; the 32 lanes touch 32 lines per load, which at ~3 loads per sample and key-chunk is nowhere near a limit).
     // No shuffles, no serial dependence between samples.
-    if (!table_has_dup) {
+    if (!table_has_dup && part == 0u) {
       uint2 rA = make_uint2(0u, 0u);
       if (active) {
         Onv<1> y;
@@ -457,15 +486,20 @@ eloc_block_kernel(const u64 *__restrict__ bra, const u32 *__restrict__ slots, co
       }
     }
     if (active) {
+      const u32 first = part * runs_per_part;
       if (h.over) {
-        c.my_runs[0] = HitRun{0u, kOverflow};
-        run_cnt[sid] = 1u;
-      } else {
-        if (h.fill) {
-          c.my_runs[h.nrun] = HitRun{h.base, h.fill};
-          ++h.nrun;
-        }
+        c.my_runs[first] = HitRun{0u, kOverflow};
+        h.nrun = first + 1u;
+      } else if (h.fill) {
+        c.my_runs[h.nrun] = HitRun{h.base, h.fill};
+        ++h.nrun;
+      }
+      if (parts == 1u) {
         run_cnt[sid] = h.nrun;
+      } else {
+        // every part leaves its unused records empty and reports all of them (the same value from every part)
+        for (u32 r = h.nrun; r < h.end; ++r) c.my_runs[r] = HitRun{0u, 0u};
+        run_cnt[sid] = (u32)run_stride;
       }
     }
     __syncwarp();
@@ -527,12 +561,17 @@ int launch_eloc_block(const u64 *bra, long long n, const GroupView &gv, char *bl
   bg.pad = g.noA > 4 ? 0u : 0xffffffffu;             // distance noA resp. 32 - noA from every alpha string
   bg.pow2 = g.noA > 4;
   const size_t smem = sizeof(BlockWarpSmem) * kBlkWarps;
-  if (cudaFuncSetAttribute(eloc_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-    return check_launch("eloc_block_kernel smem opt-in");
   long long ctas = (n + 32 * kBlkWarps - 1) / (32 * kBlkWarps);
   const long long cap = 148LL * (long long)((227 * 1024) / (sizeof(BlockWarpSmem) * kBlkWarps + 1024));
   if (ctas > cap) ctas = cap;
-  eloc_block_kernel<<<(unsigned)ctas, kBlkWarps * 32, smem, st>>>(bra, slots, tiles, ctr, gv, runs, run_cnt, run_stride, hits, self_pos, hit_cap, bg);
+  // fewer than ~2 tiles (of ~26 samples) per resident warp: split the tiles (the knob block_parts forces 1, 2 or 4 parts)
+  const int forced = eloc_tuning().block_parts;
+  const bool split = forced ? forced > 1 : n < 2 * 26 * ctas * kBlkWarps;
+  auto kern = split ? eloc_block_kernel<true> : eloc_block_kernel<false>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    return check_launch("eloc_block_kernel smem opt-in");
+  kern<<<(unsigned)ctas, kBlkWarps * 32, smem, st>>>(bra, slots, tiles, ctr, gv, runs, run_cnt, run_stride, hits, self_pos, hit_cap, bg,
+                                                     (u32)(forced == 3 ? 2 : forced));
   count_launch();
   return check_launch("eloc_block_kernel");
 }

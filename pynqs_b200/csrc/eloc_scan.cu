@@ -792,15 +792,17 @@ eloc_eval_tile_kernel(const u64 *__restrict__ bra, long long n, const double *__
                       const u64 *__restrict__ key, const double *__restrict__ psi, long long N, GroupView gv,
                       const HitRun *__restrict__ runs, const u32 *__restrict__ run_cnt, int run_stride, const u32 *__restrict__ hits,
                       const u32 *__restrict__ self_pos, const double *__restrict__ hii, double *__restrict__ eloc,
-                      double *__restrict__ psi0_out, u32 *__restrict__ heavy_list, ElocCounters *ctr, ExcGeom g) {
+                      double *__restrict__ psi0_out, u32 *__restrict__ heavy_list, ElocCounters *ctr, ExcGeom g, int per_warp) {
   __shared__ OrbLists s_lists[kEvalThreads / 32];
   __shared__ EvalTileSmem s_tile[kEvalThreads / 32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   EvalTileSmem &T = s_tile[warp];
-  const long long s0 = ((long long)blockIdx.x * (kEvalThreads / 32) + warp) * 32;
+  // per_warp: samples a warp takes (32; 16 or 8 when the call has too few samples to fill the GPU with 32 per warp -- the hit
+  // lists are walked 32 hits at a time whatever the number of samples they belong to)
+  const long long s0 = ((long long)blockIdx.x * (kEvalThreads / 32) + warp) * per_warp;
   if (s0 >= n) return;
   const long long s = s0 + lane;
-  const bool valid = s < n;
+  const bool valid = lane < per_warp && s < n;
   // ---- this lane's sample ---------------------------------------------------------------------------------------------
   Onv<L> x;
 #pragma unroll
@@ -1110,10 +1112,14 @@ static int launch_eloc_LC(const u64 *bra, long long n, const double *h1e, const 
     }
     // 32 samples per warp; calls too small to fill the GPU that way keep one warp per sample
     if ((nb >= 148LL * 32 * 8 && eloc_tuning().eval_tiles) || eloc_tuning().eval_tiles == 2) {
-      const unsigned eb = (unsigned)((nb + kEvalThreads - 1) / kEvalThreads);
+      // samples per warp: 32 (fewer per warp were measured slower even for a rank's 125 000 samples at 8 GPUs: 178 against
+      // 168 us with 8 per warp -- the per-warp bookkeeping outweighs the shorter tail)
+      const int per_warp = 32;
+      const long long per_cta = (long long)per_warp * (kEvalThreads / 32);
+      const unsigned eb = (unsigned)((nb + per_cta - 1) / per_cta);
       eloc_eval_tile_kernel<L, CPLX, HALF><<<eb, kEvalThreads, 0, st>>>(bra + b0 * L, nb, h1e, h2e, key, psi, N, gv, runs, run_cnt,
                                                                         lay.run_stride, hits, self_pos, hii + b0, eloc + b0 * w,
-                                                                        psi0 + b0 * w, heavy, ctr, g);
+                                                                        psi0 + b0 * w, heavy, ctr, g, per_warp);
       count_launch();
       // the samples with long hit lists, one warp each (a fixed grid of persistent warps reads the list's length on the device)
       const long long cap = 148LL * 12;

@@ -94,18 +94,41 @@ lut_batched_kernel(const u64 *__restrict__ key, long long N, IndexView iv, const
     const u64 diff = (x[0] ^ x[1]) | (x[0] ^ x[2]) | (x[0] ^ x[3]);
     const bool same_b = (diff & kOdd) == 0ull, same_a = (diff & kEven) == 0ull;
     const bool by_alpha = !same_b && same_a;  // the whole thread goes through the alpha-grouped directory
+    const bool mixed = !same_b && !same_a;
+    // the end of a run inside the thread's four queries (nearly every warp has such a thread: the runs are 75 rows long):
+    // ONE more probe, for the beta string of the last query, covers the queries of the second run; what matches neither
+    // (three runs in four queries: the seams between excitation classes) is probed one by one further down
+    const DirSlot *dir = by_alpha ? iv.dir[1] : iv.dir[0];
+    Onv<1> o;
+    o.w[0] = x[0];
+    const u64 h0 = hash_string<1>(o, by_alpha ? kEven : kOdd);
+    const u32 s0 = dir_first_slot(lg_dir, h0);
+    const uint4 e0 = __ldg(reinterpret_cast<const uint4 *>(dir + s0));  // (its use comes after the hashes below)
+    u64 h3 = 0ull;
+    u32 s3 = 0u;
+    uint4 e3 = make_uint4(0u, 0u, 0u, 0u);
+    if (mixed) {
+      o.w[0] = x[Q - 1];
+      h3 = hash_beta<1>(o);
+      s3 = dir_first_slot(lg_dir, h3);
+      e3 = __ldg(reinterpret_cast<const uint4 *>(iv.dir[0] + s3));
+    }
+    // ---- hashes of the OTHER string of every query (independent of the directory: they fill its latency) -----------------
+    const u64 other = by_alpha ? kOdd : kEven;  // the string the region is hashed by
+    u32 tag[Q], hiw[Q];
+#pragma unroll
+    for (int j = 0; j < Q; ++j) {
+      o.w[0] = x[j];
+      const u64 h2 = hash_string<1>(o, other);
+      tag[j] = hash_tag(h2);
+      hiw[j] = (u32)(h2 >> 32);
+    }
     {
-      Onv<1> o;
-      o.w[0] = x[0];
-      const u64 d0 = dir_find(by_alpha ? iv.dir[1] : iv.dir[0], lg_dir, hash_string<1>(o, by_alpha ? kEven : kOdd));
+      const u64 d0 = dir_resolve(dir, lg_dir, h0, s0, e0);
 #pragma unroll
       for (int j = 0; j < Q; ++j) desc[j] = d0;
-      if (!same_b && !same_a) {
-        // the end of a run inside the thread's four queries (nearly every warp has such a thread: the runs are 75 rows
-        // long): ONE more probe, for the beta string of the last query, covers the queries of the second run; what
-        // matches neither (three runs in four queries: the seams between excitation classes) is probed one by one
-        o.w[0] = x[Q - 1];
-        const u64 d3 = dir_find(iv.dir[0], lg_dir, hash_beta<1>(o));
+      if (mixed) {
+        const u64 d3 = dir_resolve(iv.dir[0], lg_dir, h3, s3, e3);
         desc[Q - 1] = d3;
 #pragma unroll
         for (int j = 1; j < Q - 1; ++j) {
@@ -118,21 +141,15 @@ lut_batched_kernel(const u64 *__restrict__ key, long long N, IndexView iv, const
         }
       }
     }
-    const u64 other = by_alpha ? kOdd : kEven;  // the string the region is hashed by
     // ---- tag buckets: four loads in flight ----------------------------------------------------------------------------
     uint4 t[Q];
-    u32 tag[Q];
 #pragma unroll
     for (int j = 0; j < Q; ++j) {
-      Onv<1> o;
-      o.w[0] = x[j];
-      const u64 h2 = hash_string<1>(o, other);
-      tag[j] = hash_tag(h2);
       t[j] = make_uint4(0u, 0u, 0u, 0u);
       const u32 off = (u32)desc[j], lg = (u32)(desc[j] >> 32);
       if ((int)lg >= 0) {  // (kNoRegion has all bits set; a real region has lg <= 31)
         // top lg bits of the high hash word = h2 >> (64 - lg), and 0 for a one-bucket region, in one funnel shift
-        const u32 bkt = __funnelshift_l((u32)(h2 >> 32), 0u, lg);
+        const u32 bkt = __funnelshift_l(hiw[j], 0u, lg);
         t[j] = __ldg(iv.pool + off + bkt);
       }
     }
@@ -141,7 +158,6 @@ lut_batched_kernel(const u64 *__restrict__ key, long long N, IndexView iv, const
     for (int j = 0; j < Q; ++j) {
       r[j] = -1;
       if (tags_match(t[j], tag[j]) || bucket_overflowed(t[j])) {  // rare: a hit, a tag collision or a full bucket
-        Onv<1> o;
         o.w[0] = x[j];
         const u64 h2 = hash_string<1>(o, other);
         r[j] = region_probe<1>(key, iv, desc[j], h2, [&]() { return o; });

@@ -161,6 +161,21 @@ __device__ __forceinline__ u64 dir_find(const DirSlot *__restrict__ dir, u32 log
   return kNoRegion;
 }
 
+// the same probe split in two, so that a caller can put independent work between the load and its use:
+// dir_first_slot / the caller's __ldg of that slot / dir_resolve (which continues the linear probing when it has to)
+__device__ __forceinline__ u32 dir_first_slot(u32 log2_dir, u64 h) { return (u32)(h >> (64 - log2_dir)); }
+__device__ __forceinline__ u64 dir_resolve(const DirSlot *__restrict__ dir, u32 log2_dir, u64 h, u32 s, uint4 e) {
+  const u32 mask = (1u << log2_dir) - 1u;
+  for (u32 probe = 0; probe <= mask; ++probe) {
+    const u64 eh = (u64)e.x | ((u64)e.y << 32);
+    if (eh == h) return (u64)e.z | ((u64)e.w << 32);
+    if (eh == kDirEmpty) return kNoRegion;
+    s = (s + 1) & mask;
+    e = __ldg(reinterpret_cast<const uint4 *>(dir + s));
+  }
+  return kNoRegion;
+}
+
 // probe the region `desc` for the string hash h2; make_key() builds the query only when a tag matches
 template <int L, typename MakeKey>
 __device__ __forceinline__ long long region_probe(const u64 *__restrict__ key, const IndexView &iv, u64 desc, u64 h2,

@@ -207,7 +207,7 @@ def _default_tuning():
     _lib.set_tuning()
 
 
-@pytest.fixture(params=["folded", "full_keys", "block", "full_keys_tiles"])
+@pytest.fixture(params=["folded", "full_keys", "block", "block_whole_tiles", "block_4_parts", "full_keys_tiles"])
 def scan_route(request):
     """One-word ONVs are scanned through folded 32-bit strings; the knob full_keys forces the full-key
     route that multi-word ONVs (and tables of 2^30 keys or more) take; "block" sends every call, however small, through
@@ -220,10 +220,13 @@ def scan_route(request):
     elif request.param == "full_keys_tiles":
         _lib.set_tuning("full_keys", 1)
         _lib.set_tuning("eval_tiles", 2)
-    elif request.param == "block":
+    elif request.param.startswith("block"):
         _lib.set_tuning("block_min_samples", 1)
         _lib.set_tuning("block_min_group", 4)
         _lib.set_tuning("eval_tiles", 2)  # ... and the evaluation kernel that takes 32 samples per warp
+        # the alpha-beta groups of a tile walked by one warp, or split over 4 ("block": the kernel's own choice, 2 for small calls)
+        if request.param != "block":
+            _lib.set_tuning("block_parts", 1 if request.param == "block_whole_tiles" else 4)
     return request.param
 
 
