@@ -481,8 +481,7 @@ def run_ours(args):
                                        "fraction -- the one-pass kernels never write comb/Hmat/idx; the kernels that really move those bytes are in "
                                        "'roofline_hbm_kernels'"}}
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        leave(world)
         return
     cfg = base_config(n_total, integrals, args.table)
     cfg.update({"method": "sample-space, one-pass kernels", "l2": "flushed between timed steps (512 MiB write)",
@@ -521,11 +520,30 @@ def run_ours(args):
     if world == 1 and not args.no_api_path:
         line["roofline_hbm_kernels"] = time_api_path(ops, dev, main["d_keys"], main["d_psi"], h1e, h2e, M, peak, prof)
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
     if not ok:
         sys.stderr.write("bench.py: PARITY FAILURE against the reference extension (see 'parity' in the JSON line)\n")
+        sys.stderr.flush()
+        if world > 1:
+            os._exit(3)
         sys.exit(3)
+    leave(world)
+
+
+def leave(world: int) -> None:
+    """End of a multi-rank run: synchronise, then exit WITHOUT destroy_process_group() -- the teardown was seen to block for
+    minutes after the symmetric-memory rendezvous of the peer-memory collectives (every rank had finished its work), and a
+    rank that never exits keeps torchrun, and whoever launched it, waiting."""
+    if world <= 1:
+        return
+    import torch
+    import torch.distributed as dist
+
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)
 
 
 def load_profile_numbers():

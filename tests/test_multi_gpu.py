@@ -20,6 +20,24 @@ def _free_port():
 
 
 def _worker(rank, world, port, n, cplx, q):
+    """One rank.  Whatever goes wrong is reported through the queue at once (the other rank would otherwise wait in a
+    collective until the parent's timeout) and the process leaves without waiting for its peer."""
+    import traceback
+
+    code = 0
+    try:
+        _worker_body(rank, world, port, n, cplx, q)
+    except BaseException:  # noqa: BLE001
+        q.put((rank, "error", traceback.format_exc()))
+        code = 1
+    # leave without tearing the process group down: destroy_process_group() was seen to block for minutes after the
+    # symmetric-memory rendezvous (both ranks had already delivered their results), which kept pytest from exiting
+    q.close()
+    q.join_thread()
+    os._exit(code)
+
+
+def _worker_body(rank, world, port, n, cplx, q):
     import torch.distributed as dist
 
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -27,7 +45,7 @@ def _worker(rank, world, port, n, cplx, q):
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
-    try:
+    if True:
         from pynqs_b200 import C_extension as ops
         from pynqs_b200 import _lib
         from pynqs_b200 import synthetic as S
@@ -60,8 +78,8 @@ def _worker(rank, world, port, n, cplx, q):
         torch.cuda.synchronize()
         q.put((rank, bool(torch.equal(torch.view_as_real(eloc) if cplx else eloc, torch.view_as_real(want) if cplx else want)),
                bool(torch.equal(torch.view_as_real(psi0) if cplx else psi0, torch.view_as_real(want0) if cplx else want0)), st["mean"], st["var"], e - b))
-    finally:
-        dist.destroy_process_group()
+    torch.cuda.synchronize()
+    dist.barrier()
 
 
 @pytest.mark.parametrize("n,cplx", [(20001, False), (6000, True)])
@@ -73,13 +91,23 @@ def test_sharded_step_equals_single_gpu(n, cplx):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, n, cplx, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, n, cplx, q), daemon=True) for r in range(2)]
     for p in procs:
         p.start()
-    res = sorted([q.get(timeout=300) for _ in range(2)], key=lambda t: t[0])
-    for p in procs:
-        p.join(timeout=60)
-        assert p.exitcode == 0
+    try:
+        res = []
+        for _ in range(2):
+            item = q.get(timeout=180)
+            assert item[1] != "error", f"rank {item[0]} failed:\n{item[2]}"
+            res.append(item)
+        res.sort(key=lambda t: t[0])
+        for p in procs:
+            p.join(timeout=60)
+            assert p.exitcode == 0
+    finally:  # never leave a rank behind that waits for its peer (it would keep pytest from exiting)
+        for p in procs:
+            if p.is_alive():
+                p.kill()
     assert all(r[1] and r[2] for r in res), res
     assert res[0][3] == res[1][3] and res[0][4] == res[1][4]  # the same statistics on every rank
     assert res[0][5] + res[1][5] == n
