@@ -186,8 +186,11 @@ def main():
         line["api_kernels"] = api
     if rank == 0:
         print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    if world > 1:  # (no destroy_process_group: it can block after the symmetric-memory rendezvous -- see bench.leave)
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

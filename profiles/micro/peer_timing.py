@@ -43,4 +43,9 @@ outs = torch.zeros(7 * world, dtype=torch.float64, device=dev)
 res["nccl_small_all_gather_us"] = t(lambda: dist.all_gather_into_tensor(outs, small))
 if rank == 0:
     print(world, {k: round(v, 1) for k, v in res.items()}, flush=True)
-dist.destroy_process_group()
+torch.cuda.synchronize()
+dist.barrier()
+import os, sys  # noqa: E401,E402
+
+sys.stdout.flush()
+os._exit(0)  # (no destroy_process_group: it can block after the symmetric-memory rendezvous)
