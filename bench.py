@@ -624,7 +624,7 @@ def time_api_path(ops, dev, d_keys, d_psi, h1e, h2e, M, peak, prof, chunk=32768,
          "peak": peak, "unit": "GB/s", "frac": fb / f_ms / 1e6 / peak, "traffic": prof.get("enumerate_dram_bytes_per_launch"),
          "algorithmic_bytes_per_launch": fb, "samples_per_launch": chunk, "ms": f_ms, "samples_per_s": chunk / f_ms * 1e3,
          "vs_reference_cuda": ref_cuda.get("fused", ref_cuda)},
-        {"bound": "hbm", "kernel": "lut_indexed_kernel<1> = wavefunction_lut", "achieved": lb / l_ms / 1e6, "peak": peak,
+        {"bound": "hbm", "kernel": "lut_batched_kernel (four consecutive queries per thread) = wavefunction_lut", "achieved": lb / l_ms / 1e6, "peak": peak,
          "unit": "GB/s", "frac": lb / l_ms / 1e6 / peak, "traffic": prof.get("lut_dram_bytes_per_launch"),
          "algorithmic_bytes_per_launch": lb, "samples_per_launch": chunk, "ms": l_ms, "samples_per_s": chunk / l_ms * 1e3,
          "vs_reference_cuda": ref_cuda.get("lut", ref_cuda)},

@@ -235,7 +235,9 @@ int pynqs_weighted_moments(const void *eloc, int eloc_complex, const void *weigh
  * multi-word ONVs), "block_enable" (0: per-sample kernel only), "block_min_samples" (calls with fewer samples use the
  * per-sample kernel only, default 4096), "block_min_group" (samples sharing a beta string needed for a tile of the
  * block kernel, default 8), "eval_tiles" (evaluation kernel: 0 one warp per sample, 1 = default: 32 samples per warp for
- * large calls, 2: for every call).  name == NULL restores every default.  The scratch size of pynqs_eloc_scratch_bytes
+ * large calls, 2: for every call), "block_parts" (block kernel: 0 = by the size of the call, 1 / 2 / 4: parts the groups
+ * of a tile are split into), "lut_pipeline" (wavefunction_lut on one-word ONVs: 1 = default, four consecutive queries per
+ * thread; 0: one query per thread).  name == NULL restores every default.  The scratch size of pynqs_eloc_scratch_bytes
  * depends on the knobs: set them before sizing the scratch. */
 int pynqs_set_tuning(const char *name, int64_t value);
 
