@@ -496,6 +496,40 @@ def test_fe2s2_shape_at_scale_properties(scan_route):
     np.testing.assert_allclose(e1[:8].cpu().numpy(), want, rtol=1e-12, atol=0)
 
 
+@pytest.mark.parametrize("table", ["uniform", "zipf0.8"])
+def test_headline_size_table_against_the_oracle(table):
+    """The benchmarked configuration itself -- 10^6 unique Fe2S2 samples that are their own table, the reference's Fe2S2
+    integrals -- and its Zipf-skewed variant (beta strings with thousands of samples next to strings with a handful): E_loc
+    of ALL samples on the GPU, an oracle subsample spread over the table plus, for the skewed table, samples of the heaviest
+    beta strings (the long groups, the long hit lists, the warp-per-sample evaluation route)."""
+    import bench
+
+    f = fe2s2()
+    sorb, noA, noB, nele = int(f["sorb"]), int(f["noA"]), int(f["noB"]), int(f["nele"])
+    keys = bench.make_table(table, 1_000_000)
+    n = keys.shape[0]
+    psi = S.random_psi(n, seed=1235)
+    h1e_np, h2e_np = np.ascontiguousarray(f["h1e"]), np.ascontiguousarray(f["h2e"])
+    lut = WavefunctionLUT(dev(keys), dev(psi), sorb, DEV, rank=0, world_size=1)
+    eloc, _, psi_x = local_energy_sample_space(lut.bra_key, dev(h1e_np), dev(h2e_np), lut, sorb, nele, noA, noB)
+    e = eloc.cpu().numpy()
+    assert np.isfinite(e).all()
+    assert torch.equal(psi_x, lut.wf_value)
+    skeys, spsi = lut.bra_key.cpu().numpy(), lut.wf_value.cpu().numpy()
+    words = skeys.view(np.uint64).reshape(-1)
+    assert (words[1:] > words[:-1]).all()  # the table the oracle searches is the sorted unique set
+    pick = list(range(0, n, n // 16))[:16]
+    if table != "uniform":
+        beta = words & np.uint64(0xAAAAAAAAAAAAAAAA)
+        vals, counts = np.unique(beta, return_counts=True)
+        for b in vals[np.argsort(counts)[-3:]]:  # the three heaviest beta strings: two samples of each
+            pick += list(np.nonzero(beta == b)[0][[0, -1]])
+        assert counts.max() > 2000
+    pick = np.array(sorted(set(int(i) for i in pick)))
+    want = O.eloc_sample_space(skeys[pick], h1e_np, h2e_np, skeys, spsi, sorb, nele, noA, noB)
+    np.testing.assert_allclose(e[pick], want, rtol=1e-12, atol=0)
+
+
 def test_row_index_beyond_int32():
     """n * M > 2^31 rows in one call (the reference's int indexing overflows here, kernel.cu:190,220)."""
     sorb, noA, noB, nele = 40, 15, 15, 30
