@@ -543,6 +543,7 @@ def leave(world: int) -> None:
     torch.cuda.synchronize()
     sys.stdout.flush()
     sys.stderr.flush()
+    time.sleep(0.5)  # the peers may still be completing their side of the barrier: do not pull the memory from under them
     os._exit(0)
 
 
