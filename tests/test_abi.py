@@ -101,3 +101,23 @@ def test_libs_c_extension_exposes_the_reference_names():
     assert list(inspect.signature(ext.get_comb_tensor).parameters) == ["bra", "sorb", "nele", "noA", "noB", "flag_bit"]
     assert list(inspect.signature(ext.get_hij_torch).parameters) == ["bra", "ket", "h1e", "h2e", "sorb", "nele"]
     assert list(inspect.signature(ext.wavefunction_lut).parameters)[:4] == ["bra_key", "onv", "sorb", "little_endian"]
+
+
+def test_every_tuning_knob_is_documented_and_settable(lib):
+    """The knob table of pynqs_set_tuning (csrc/abi.cu) and its description in the header list the same names; every knob
+    accepts its default-range value without a GPU, an unknown name or an out-of-range value is EVALUE."""
+    src = open(os.path.join(ROOT, "pynqs_b200", "csrc", "abi.cu")).read()
+    table = src[src.index("} knobs[] = {"): src.index("if (name == nullptr)")]
+    knobs = re.findall(r'\{"([a-z_]+)",\s*&t\.', table)
+    assert len(knobs) >= 9 and len(set(knobs)) == len(knobs)
+    header = open(os.path.join(ROOT, "include", "pynqs_b200.h")).read()
+    doc = header[header.index("Test / experiment knobs"): header.index("int pynqs_set_tuning")]
+    for k in knobs:
+        assert f'"{k}"' in doc, f"knob {k} is missing from include/pynqs_b200.h"
+    try:
+        for k, v in (("block_parts", 2), ("lut_pipeline", 0), ("eval_tiles", 2), ("block_min_group", 4)):
+            assert lib.pynqs_set_tuning(k.encode(), ctypes.c_int64(v)) == 0
+        assert lib.pynqs_set_tuning(b"block_parts", ctypes.c_int64(5)) == _lib.EVALUE
+        assert lib.pynqs_set_tuning(b"no_such_knob", ctypes.c_int64(1)) == _lib.EVALUE
+    finally:
+        assert lib.pynqs_set_tuning(None, ctypes.c_int64(0)) == 0
