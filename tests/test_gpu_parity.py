@@ -151,6 +151,29 @@ def test_lookup_classic_and_hashed_equal_oracle(L, sorb, na):
     np.testing.assert_array_equal(sort_onv(dev(keys)).cpu().numpy(), order)
 
 
+@pytest.mark.parametrize("n_q,shift", [(10003, 0), (10002, 0), (9001, 1), (3, 0)])
+def test_lookup_hashed_tails_and_unaligned_queries(n_q, shift):
+    """The four-queries-per-thread kernel takes n - n % 4 queries of a one-word lookup, the one-query kernel the rest, and all
+    of them when the query tensor is not 16-byte aligned (a view that starts one row into its storage).  Queries in runs
+    that share a beta or an alpha string (rows of comb) and random ones, against the oracle."""
+    sorb, na = 40, 15
+    keys = S.random_onvs(30000, sorb, na, na, seed=90)
+    skeys = keys[O.sort_onv(keys)]
+    comb, _ = ops.get_comb_tensor(dev(keys[:2]), sorb, 2 * na, na, na, False)     # runs of shared strings; row 0 of each is a hit
+    rng = np.random.default_rng(91)
+    pool = np.concatenate([comb.cpu().numpy().reshape(-1, 8), keys[rng.permutation(len(keys))[:3000]], S.random_onvs(3000, sorb, na, na, seed=92)])
+    q = np.ascontiguousarray(pool[shift : shift + n_q])
+    assert q.shape[0] == n_q
+    want_idx, want_mask = O.lut(skeys, q)
+    dk = dev(skeys)
+    dq = dev(pool)[shift : shift + n_q]           # shift = 1: data pointer 8 bytes into the storage
+    assert dq.is_contiguous() and (dq.data_ptr() % 16 == 8) == (shift == 1)
+    idx, mask = ops.wavefunction_lut(dk, dq, sorb, hash_index=ops.HashIndex(dk))
+    np.testing.assert_array_equal(idx.cpu().numpy(), want_idx)
+    np.testing.assert_array_equal(mask.cpu().numpy(), want_mask)
+    assert int(want_mask.sum()) >= 1
+
+
 def test_lookup_golden_through_lut_mirror():
     g = load("lut_lookup_l1")
     rng = np.random.default_rng(31)
