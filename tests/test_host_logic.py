@@ -84,3 +84,31 @@ def test_random_onvs_have_fixed_occupation():
     bits = np.unpackbits(x, axis=1, bitorder="little")[:, :100]
     assert (bits[:, 0::2].sum(1) == 25).all() and (bits[:, 1::2].sum(1) == 25).all()
     assert len({bytes(r) for r in x}) == 256
+
+
+def test_bench_host_helpers():
+    """bench.py's host side: the algorithmic byte count of SURVEY.md 8(d), the parity block (tolerances, weights), the
+    seeded tables (unique rows, fixed occupation, the skew of the Zipf variant) -- no GPU involved."""
+    import bench
+
+    assert bench.algorithmic_bytes_per_sample(7876, 1) == 259924            # Fe2S2, SURVEY.md 8(d)
+    assert bench.algorithmic_bytes_per_sample(571876, 2, 16) == 16 + 571876 * 49 + 16
+    psi = np.array([1.0, 2.0, -1.0, 0.5])
+    ref = np.array([-1.0, -2.0, -3.0, -4.0])
+    ok = bench.parity_block(ref * (1 + 1e-15), ref, psi, "x")
+    assert ok["ok"] and ok["n"] == 4 and ok["max_rel_err"] < 1e-14 and ok["mean_energy_abs_diff_ha"] < 1e-13
+    w = psi ** 2 / np.sum(psi ** 2)
+    assert abs(ok["mean_energy_ha"] - float(np.sum(w * ref))) < 1e-15
+    bad = bench.parity_block(ref * np.array([1, 1, 1 + 1e-9, 1]), ref, psi, "x")
+    assert not bad["ok"] and bad["max_rel_err"] > 1e-10
+    assert not bench.parity_block(np.array([np.nan, -2, -3, -4.0]), ref, psi, "x")["ok"]
+    for kind in ("uniform", "zipf0.8"):
+        keys = bench.make_table(kind, 20000)
+        words = keys.view(np.uint64).reshape(-1)
+        assert keys.shape == (20000, 8) and np.unique(words).size == 20000
+        bits = np.unpackbits(keys, axis=1, bitorder="little")
+        assert (bits[:, 0:40:2].sum(1) == 15).all() and (bits[:, 1:40:2].sum(1) == 15).all() and not bits[:, 40:].any()
+        beta_counts = np.unique(words & np.uint64(0xAAAAAAAAAAAAAAAA), return_counts=True)[1]
+        if kind != "uniform":
+            assert beta_counts.max() > 20 * np.median(beta_counts)           # a few heavy strings, many light ones
+        np.testing.assert_array_equal(keys, bench.make_table(kind, 20000))   # seeded
